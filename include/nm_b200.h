@@ -169,6 +169,8 @@ int  nm_exchange(nm_engine* h, const double* uniforms, int64_t cycle,
 /* counters (for the roofline figures): out[NM_COUNTER_WIDTH] */
 int  nm_get_counters(nm_engine* h, uint64_t* out);
 int  nm_reset_counters(nm_engine* h);
+/* number of kernels this engine has launched since nm_create (bench.py: gpu_launches) */
+int64_t nm_launch_count(nm_engine* h);
 
 /* ---- a-14: calculate_rdf (lammps_distr.py:123-135) over a batch of samples.
  *   pos   : HOST or DEVICE float32 [nsamples][natoms][3] (dev_ptrs selects which)
@@ -187,6 +189,10 @@ int  nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs,
  *      buf may be NULL to query the size. */
 int64_t nm_format_thrm(const double* vals17, char* buf, int64_t cap);
 int64_t nm_format_traj(int32_t natoms, double box, const double* x, char* buf, int64_t cap);
+/* nrep trajectory records formatted by nthreads host threads and packed back to back in replica
+ * order; out_off[nrep+1] receives the byte offsets. box: [nrep], x: [nrep][3*natoms]. */
+int64_t nm_format_traj_batch(int32_t nrep, int32_t natoms, const double* box, const double* x,
+                             char* buf, int64_t cap, int64_t* out_off, int32_t nthreads);
 
 /* ---- roofline denominators: sustained FMA issue rate of this device, measured
  *      with a dependent-chain-free FMA kernel. Returns FLOP/s (2 per FMA). */

@@ -1,0 +1,1099 @@
+// nm_engine.cu -- replica-exchange NPT Monte Carlo engine for sm_100a (B200), C-ABI in include/nm_b200.h.
+//
+// One CTA owns one replica configuration for a whole collection cycle (MOD moves): positions
+// stay in shared memory, the LJ lj/cut evaluation runs off a Verlet list held in HBM/L2, all
+// NSTPS velocity-Verlet steps of an HMC trajectory, the Metropolis tests and the counters
+// happen on chip. Replaces the per-replica LAMMPS instance of lammps_remcmc.py:459-691.
+// FP64 FMA pipe is the roofline (no tensor cores: not a dense contraction).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "nm_b200.h"
+#include "nm_device.cuh"
+
+namespace nm {
+
+constexpr int NCMAX = 8;                 // cell grid is at most 8^3
+constexpr int RED_DOUBLES = 32 * 12 + 12;
+constexpr int BC_DOUBLES = 32;
+constexpr int ST_BOX = 1, ST_NEIGH = 2;  // status bits
+
+// ------------------------------------------------------------------ device-side engine description
+struct Dev {
+  int N, Npad, nrep, nrep_global, rep_offset, nt, maxq;   // maxq = list capacity in quads
+  int nstps, mod, bulk, text_rounding;
+  double ppos, pvol, lat, mass, rc, skin;
+  uint32_t seed_lo, seed_hi;
+  // per configuration
+  double *x, *v, *f, *xs, *vs, *fs, *x0;   // [nrep][3][Npad]
+  ushort4* list;                           // [nrep][maxq][Npad]
+  uint16_t* nnb;                           // [nrep][Npad]
+  double *box, *pe, *w, *ke, *L0;          // [nrep]
+  double *step;                            // [nrep][3]  dx dv dt
+  double *cnt;                             // [nrep][6]  ntp nap ntv nav nth nah
+  double *list_pairs;                      // [nrep] listed unordered pairs of the current list
+  int *cfg_slot, *slot_cfg;                // local permutation
+  int *status;                             // [nrep]
+  // per local slot
+  double *label;                           // [nrep][4] et pf temp temp_vel
+  double *thermo;                          // [nrep][18]
+  unsigned long long* counters;            // [NM_COUNTER_WIDTH]
+};
+
+// per-CTA context (registers + shared-memory carve)
+struct Ctx {
+  int N, Npad, c;
+  double L, L0, thr2;           // box, list build box, squared displacement budget (build-box units)
+  double *sx, *sy, *sz;         // shared positions
+  double *red, *bc;             // reduction scratch, broadcast scratch
+  int *cell_cnt, *cell_start, *ibc;
+  uint16_t *cell_atoms, *atom_cell;
+  unsigned long long* s_pairs;  // shared: in-cutoff ordered pairs of force-only evaluations
+  // global views of this configuration
+  double *gx, *gv, *gf, *gxs, *gvs, *gfs, *gx0;
+  ushort4* list; uint16_t* nnb;
+  unsigned long long ct[NM_COUNTER_WIDTH];   // meaningful on thread 0 only
+  double list_pairs;
+  int status;
+};
+
+__host__ __device__ inline size_t smem_bytes(int Npad) {
+  size_t b = sizeof(double) * (3 * (size_t)Npad + RED_DOUBLES + BC_DOUBLES);
+  b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8);
+  b += sizeof(unsigned long long) * 2;
+  b += sizeof(uint16_t) * 2 * (size_t)Npad;
+  return b;
+}
+
+__device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned char* smem) {
+  cx.N = d.N; cx.Npad = d.Npad; cx.c = c;
+  double* p = reinterpret_cast<double*>(smem);
+  cx.sx = p; cx.sy = p + d.Npad; cx.sz = p + 2 * d.Npad; p += 3 * d.Npad;
+  cx.red = p; p += RED_DOUBLES;
+  cx.bc = p; p += BC_DOUBLES;
+  cx.s_pairs = reinterpret_cast<unsigned long long*>(p); p += 2;
+  int* q = reinterpret_cast<int*>(p);
+  cx.cell_cnt = q; q += NCMAX * NCMAX * NCMAX + 1;
+  cx.cell_start = q; q += NCMAX * NCMAX * NCMAX + 1;
+  cx.ibc = q; q += 8;
+  uint16_t* h = reinterpret_cast<uint16_t*>(q);
+  cx.cell_atoms = h; cx.atom_cell = h + d.Npad;
+  const size_t off = (size_t)c * 3 * d.Npad;
+  cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
+  cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off; cx.gx0 = d.x0 + off;
+  cx.list = d.list + (size_t)c * d.maxq * d.Npad;
+  cx.nnb = d.nnb + (size_t)c * d.Npad;
+  cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.list_pairs = d.list_pairs[c];
+  cx.status = 0;
+  for (int k = 0; k < NM_COUNTER_WIDTH; k++) cx.ct[k] = 0;
+  if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; }
+}
+
+// displacement budget of the current list for box L: s*(rl - 2u) >= rc, s = L/L0
+__device__ __forceinline__ void update_thr(const Dev& d, Ctx& cx) {
+  if (cx.L0 <= 0.0) { cx.thr2 = -1.0; return; }
+  const double s = cx.L / cx.L0, rl = d.rc + d.skin;
+  const double thr = 0.5 * (rl - d.rc / s) * (1.0 - 1e-9);
+  cx.thr2 = thr > 0.0 ? thr * thr : -1.0;
+}
+// squared displacement of (x,y,z) from the list reference of atom i, in build-box length units
+__device__ __forceinline__ double disp2(const Ctx& cx, int i, double x, double y, double z, double invL) {
+  double ux = x * invL - cx.gx0[i], uy = y * invL - cx.gx0[cx.Npad + i], uz = z * invL - cx.gx0[2 * cx.Npad + i];
+  ux -= rint(ux); uy -= rint(uy); uz -= rint(uz);
+  return (ux * ux + uy * uy + uz * uz) * cx.L0 * cx.L0;
+}
+
+// positions global -> shared (wrapped), plus the far-away dummy atom that pads the list
+__device__ void load_positions(const Dev& d, Ctx& cx) {
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+    cx.sx[i] = wrap1(cx.gx[i], cx.L); cx.sy[i] = wrap1(cx.gx[cx.Npad + i], cx.L); cx.sz[i] = wrap1(cx.gx[2 * cx.Npad + i], cx.L);
+  }
+  for (int i = cx.N + threadIdx.x; i < cx.Npad; i += blockDim.x) { cx.sx[i] = 1e9; cx.sy[i] = 1e9; cx.sz[i] = 1e9; }
+}
+__device__ void store_positions(Ctx& cx) {
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+    cx.gx[i] = cx.sx[i]; cx.gx[cx.Npad + i] = cx.sy[i]; cx.gx[2 * cx.Npad + i] = cx.sz[i];
+  }
+}
+
+// ------------------------------------------------------------------ Verlet list build (cell binned, deterministic)
+__device__ void build_list(const Dev& d, Ctx& cx) {
+  const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
+  const double L = cx.L, hL = 0.5 * L, rl = d.rc + d.skin, rl2 = rl * rl, invL = 1.0 / L;
+  int nc = (int)floor(L / rl);
+  if (nc > NCMAX) nc = NCMAX;
+  if (nc < 3) nc = 1;
+  const int ncell = nc * nc * nc;
+  __syncthreads();
+  if (nc > 1) {
+    for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += nthr) {
+      int a = min(nc - 1, (int)(cx.sx[i] * invL * nc)), b = min(nc - 1, (int)(cx.sy[i] * invL * nc)),
+          e = min(nc - 1, (int)(cx.sz[i] * invL * nc));
+      int c = (a * nc + b) * nc + e;
+      cx.atom_cell[i] = (uint16_t)c;
+      atomicAdd(&cx.cell_cnt[c], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int per = (ncell + 31) / 32, base = tid * per;
+      int s = 0;
+      for (int q = 0; q < per; q++) if (base + q < ncell) s += cx.cell_cnt[base + q];
+      int incl = s;
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+      int run = incl - s;
+      for (int q = 0; q < per; q++) if (base + q < ncell) { cx.cell_start[base + q] = run; run += cx.cell_cnt[base + q]; }
+      if (tid == 31) cx.cell_start[ncell] = incl;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += nthr) {
+      int c = cx.atom_cell[i];
+      int p = atomicAdd(&cx.cell_cnt[c], 1);
+      cx.cell_atoms[cx.cell_start[c] + p] = (uint16_t)i;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncell; c += nthr) {          // ascending ids inside each cell -> deterministic list order
+      const int s = cx.cell_start[c], e = cx.cell_start[c + 1];
+      for (int p = s + 1; p < e; p++) {
+        uint16_t key = cx.cell_atoms[p]; int q = p - 1;
+        while (q >= s && cx.cell_atoms[q] > key) { cx.cell_atoms[q + 1] = cx.cell_atoms[q]; q--; }
+        cx.cell_atoms[q + 1] = key;
+      }
+    }
+    __syncthreads();
+  }
+  const int maxnb = d.maxq * 4;
+  uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
+  double tot = 0.0; int over = 0;
+  for (int i = tid; i < N; i += nthr) {
+    const double xi = cx.sx[i], yi = cx.sy[i], zi = cx.sz[i];
+    int cnt = 0;
+    auto test = [&](int j) {
+      if (j == i) return;
+      double dx = mic_exact(xi - cx.sx[j], L, hL), dy = mic_exact(yi - cx.sy[j], L, hL), dz = mic_exact(zi - cx.sz[j], L, hL);
+      if (dx * dx + dy * dy + dz * dz < rl2) {
+        if (cnt < maxnb) l16[((size_t)(cnt >> 2) * Npad + i) * 4 + (cnt & 3)] = (uint16_t)j;
+        cnt++;
+      }
+    };
+    if (nc == 1) {
+      for (int j = 0; j < N; j++) test(j);
+    } else {
+      const int ci = cx.atom_cell[i], a = ci / (nc * nc), b = (ci / nc) % nc, e = ci % nc;
+      for (int da = -1; da <= 1; da++) for (int db = -1; db <= 1; db++) for (int de = -1; de <= 1; de++) {
+        const int cc = (((a + da + nc) % nc) * nc + (b + db + nc) % nc) * nc + (e + de + nc) % nc;
+        const int s = cx.cell_start[cc], en = cx.cell_start[cc + 1];
+        for (int p = s; p < en; p++) test(cx.cell_atoms[p]);
+      }
+    }
+    if (cnt > maxnb) { over = 1; cnt = maxnb; }
+    for (int k = cnt; k < ((cnt + 3) & ~3); k++) l16[((size_t)(k >> 2) * Npad + i) * 4 + (k & 3)] = (uint16_t)N;
+    cx.nnb[i] = (uint16_t)cnt;
+    tot += cnt;
+    cx.gx0[i] = xi * invL; cx.gx0[Npad + i] = yi * invL; cx.gx0[2 * Npad + i] = zi * invL;
+  }
+  double r[2] = { tot, (double)over };
+  block_sum<2>(r, cx.red);
+  cx.list_pairs = 0.5 * r[0];
+  if (r[1] > 0.0) cx.status |= ST_NEIGH;
+  cx.L0 = L;
+  update_thr(d, cx);
+  if (tid == 0) cx.ct[NM_CT_LIST_BUILDS]++;
+}
+
+// barrier after a position update; rebuilds the list if any thread saw its budget exceeded
+__device__ __forceinline__ void sync_and_maybe_build(const Dev& d, Ctx& cx, int flag) {
+  if (__syncthreads_or(flag)) build_list(d, cx);
+}
+// generic pass: is every atom still inside the displacement budget?
+__device__ void check_list(const Dev& d, Ctx& cx) {
+  int flag = cx.thr2 < 0.0;
+  if (!flag) {
+    const double invL = 1.0 / cx.L;
+    for (int i = threadIdx.x; i < cx.N; i += blockDim.x)
+      flag |= disp2(cx, i, cx.sx[i], cx.sy[i], cx.sz[i], invL) > cx.thr2;
+  }
+  sync_and_maybe_build(d, cx, flag);
+}
+
+// ------------------------------------------------------------------ a-1: LJ lj/cut evaluation off the list
+// EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
+// half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
+// Ends with a barrier: shared positions may be rewritten afterwards.
+template <bool EW, bool KICK>
+__device__ void eval_forces(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
+  const int N = cx.N, Npad = cx.Npad;
+  const double rc2 = d.rc * d.rc;
+  const int L_hi = __double2hiint(cx.L), L_lo = __double2loint(cx.L), hL_hi = __double2hiint(0.5 * cx.L);
+  double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double xi = cx.sx[i], yi = cx.sy[i], zi = cx.sz[i];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    const int nq = (cx.nnb[i] + 3) >> 2;
+    const ushort4* lp = cx.list + i;
+    ushort4 cur = nq > 0 ? lp[0] : make_ushort4(0, 0, 0, 0);
+    for (int q = 0; q < nq; q++) {
+      const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
+      const int jj[4] = { cur.x, cur.y, cur.z, cur.w };
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int j = jj[t];
+        const double dx = mic_fast(xi - cx.sx[j], L_hi, L_lo, hL_hi);
+        const double dy = mic_fast(yi - cx.sy[j], L_hi, L_lo, hL_hi);
+        const double dz = mic_fast(zi - cx.sz[j], L_hi, L_lo, hL_hi);
+        const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
+        const bool in = rsq < rc2;
+        const double r2inv = rcp_nr(rsq);
+        const double r6inv = r2inv * r2inv * r2inv;
+        const double fpair = in ? r6inv * (48.0 * r6inv - 24.0) * r2inv : 0.0;
+        fx = fma(dx, fpair, fx); fy = fma(dy, fpair, fy); fz = fma(dz, fpair, fz);
+        np += in;
+        if (EW) { e += in ? r6inv * (4.0 * r6inv - 4.0) : 0.0; vir = fma(rsq, fpair, vir); }
+      }
+      cur = nxt;
+    }
+    cx.gf[i] = fx; cx.gf[Npad + i] = fy; cx.gf[2 * Npad + i] = fz;
+    if (KICK) {
+      const double vx = fma(dtf, fx, cx.gv[i]), vy = fma(dtf, fy, cx.gv[Npad + i]), vz = fma(dtf, fz, cx.gv[2 * Npad + i]);
+      cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+      if (EW) ke += vx * vx + vy * vy + vz * vz;
+    }
+  }
+  if (EW) {
+    double r[4] = { 0.5 * e, 0.5 * vir, (double)np, ke };
+    block_sum<4>(r, cx.red);
+    out[0] = r[0]; out[1] = r[1]; out[2] = 0.5 * r[2]; out[3] = 0.5 * d.mass * r[3];
+    if (threadIdx.x == 0) {
+      cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_PAIRS_FULL] += (unsigned long long)out[2];
+      cx.ct[NM_CT_LIST_PAIRS] += (unsigned long long)cx.list_pairs;
+    }
+  } else {
+    np = __reduce_add_sync(0xffffffffu, np);
+    if ((threadIdx.x & 31) == 0) atomicAdd(cx.s_pairs, (unsigned long long)np);
+    if (threadIdx.x == 0) { cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_LIST_PAIRS] += (unsigned long long)cx.list_pairs; }
+    __syncthreads();
+  }
+}
+
+// the acceptance rule shared by all moves (lammps_remcmc.py:487-500, 532-547, 578-593, 623-638)
+__device__ __forceinline__ bool metropolis(double de, const Rng& r, uint32_t index, uint32_t purpose) {
+  const double m = exp(-de);
+  if (isinf(m) || isnan(m)) return false;
+  const double u = rng_uniform(r, index, purpose);
+  return u <= (m < 1.0 ? m : 1.0);
+}
+// thread 0 decides, everybody learns
+__device__ __forceinline__ bool broadcast_flag(Ctx& cx, bool v) {
+  __syncthreads();
+  if (threadIdx.x == 0) cx.ibc[0] = v;
+  __syncthreads();
+  return cx.ibc[0] != 0;
+}
+
+struct Energy { double pe, w; };
+
+__device__ void save_xf(Ctx& cx, bool with_v) {
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int o = a * cx.Npad + i;
+      cx.gxs[o] = (a == 0 ? cx.sx : a == 1 ? cx.sy : cx.sz)[i];
+      cx.gfs[o] = cx.gf[o];
+      if (with_v) cx.gvs[o] = cx.gv[o];
+    }
+  }
+}
+__device__ void restore_xf(Ctx& cx, bool with_v) {
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const int o = a * cx.Npad + i;
+      (a == 0 ? cx.sx : a == 1 ? cx.sy : cx.sz)[i] = cx.gxs[o];
+      cx.gf[o] = cx.gfs[o];
+      if (with_v) cx.gv[o] = cx.gvs[o];
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ a-7 bulk_position_mc (lammps_remcmc.py:477-502)
+__device__ void bulk_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double dxs, Energy& en, double* cnt) {
+  save_xf(cx, false);
+  const double dmax = d.text_rounding ? round6(dxs * d.lat) : dxs * d.lat;     // 'displace_atoms all random %f'
+  const double invL = 1.0 / cx.L;
+  int flag = cx.thr2 < 0.0;
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+    double u[3]; rng_uniform3(r, (uint32_t)i, P_BULK_DISP, u);
+    const double x = wrap1(cx.sx[i] + dmax * 2.0 * (u[0] - 0.5), cx.L), y = wrap1(cx.sy[i] + dmax * 2.0 * (u[1] - 0.5), cx.L),
+                 z = wrap1(cx.sz[i] + dmax * 2.0 * (u[2] - 0.5), cx.L);
+    cx.sx[i] = x; cx.sy[i] = y; cx.sz[i] = z;
+    if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
+  }
+  sync_and_maybe_build(d, cx, flag);
+  double o[4]; eval_forces<true, false>(d, cx, 0.0, o);
+  bool acc = false;
+  if (threadIdx.x == 0) {
+    const double de = o[0] / et - en.pe / et;
+    acc = metropolis(de, r, 0, P_BULK_ACC);
+    cnt[0] += 1.0; if (acc) cnt[1] += 1.0;
+    cx.ct[NM_CT_PMC_MOVES]++; cx.ct[NM_CT_PMC_TRIALS]++;
+  }
+  acc = broadcast_flag(cx, acc);
+  if (acc) { en.pe = o[0]; en.w = o[1]; } else restore_xf(cx, false);
+}
+
+// ------------------------------------------------------------------ a-6 volume_mc (lammps_remcmc.py:552-595)
+__device__ void volume_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double pf, double dvs, Energy& en, double* cnt) {
+  save_xf(cx, false);
+  const double box = cx.L;
+  if (threadIdx.x == 0) {
+    const double vol = pow(box, 3.0);
+    const double volnew = exp(log(vol) + 2 * (rng_uniform(r, 0, P_VMC_PROP) - 0.5) * dvs);
+    const double boxnew = cbrt(volnew);
+    cx.bc[0] = vol; cx.bc[1] = volnew; cx.bc[2] = boxnew / box;
+    cx.bc[3] = d.text_rounding ? round6(boxnew) : boxnew;                      // 'change_box ... %f'
+  }
+  __syncthreads();
+  const double vol = cx.bc[0], volnew = cx.bc[1], scale = cx.bc[2], Lnew = cx.bc[3];
+  const bool box_ok = Lnew >= 2.0 * d.rc * (1.0 + 1e-5);
+  bool acc = false;
+  double o[4] = { 0, 0, 0, 0 };
+  if (box_ok) {
+    cx.L = Lnew; update_thr(d, cx);
+    const double invL = 1.0 / Lnew;
+    int flag = cx.thr2 < 0.0;
+    for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+      const double x = wrap1(scale * cx.sx[i], Lnew), y = wrap1(scale * cx.sy[i], Lnew), z = wrap1(scale * cx.sz[i], Lnew);
+      cx.sx[i] = x; cx.sy[i] = y; cx.sz[i] = z;
+      if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
+    }
+    sync_and_maybe_build(d, cx, flag);
+    eval_forces<true, false>(d, cx, 0.0, o);
+  } else {
+    cx.status |= ST_BOX;
+  }
+  if (threadIdx.x == 0) {
+    if (box_ok) {
+      const double dh = (o[0] / et - en.pe / et) + pf * (volnew - vol) - (cx.N + 1) * log(volnew / vol);
+      acc = metropolis(dh, r, 0, P_VMC_ACC);
+    }
+    cnt[2] += 1.0; if (acc) cnt[3] += 1.0;
+    cx.ct[NM_CT_VMC_MOVES]++;
+  }
+  acc = broadcast_flag(cx, acc);
+  if (acc) { en.pe = o[0]; en.w = o[1]; }
+  else { cx.L = box; update_thr(d, cx); if (box_ok) restore_xf(cx, false); }
+}
+
+// ------------------------------------------------------------------ a-4 velocity create + zero linear + zero angular
+// LAMMPS 'velocity all create T seed dist gaussian' (loop all, mom yes, rot no), then 'zero linear',
+// 'zero angular' (lammps_remcmc.py:604-606). Returns KE = 0.5 m sum v^2.
+__device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_target) {
+  const int N = cx.N, Npad = cx.Npad;
+  const double m = d.mass, inv = 1.0 / sqrt(m);
+  double s[4] = { 0, 0, 0, 0 };
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double g[3]; rng_gauss3(r, (uint32_t)i, P_HMC_VEL, g);
+    const double vx = g[0] * inv, vy = g[1] * inv, vz = g[2] * inv;
+    cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+    s[0] += m * vx; s[1] += m * vy; s[2] += m * vz;
+  }
+  block_sum<4>(s, cx.red);
+  double vcm[3] = { s[0] / (m * N), s[1] / (m * N), s[2] / (m * N) };
+  double t[1] = { 0 };
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double vx = cx.gv[i] - vcm[0], vy = cx.gv[Npad + i] - vcm[1], vz = cx.gv[2 * Npad + i] - vcm[2];
+    cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+    t[0] += vx * vx + vy * vy + vz * vz;
+  }
+  block_sum<1>(t, cx.red);
+  const double tinst = m * t[0] / (3.0 * N - 3.0), fac = sqrt(t_target / tinst);
+  s[0] = s[1] = s[2] = s[3] = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double vx = cx.gv[i] * fac, vy = cx.gv[Npad + i] * fac, vz = cx.gv[2 * Npad + i] * fac;
+    cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+    s[0] += m * vx; s[1] += m * vy; s[2] += m * vz;
+  }
+  block_sum<4>(s, cx.red);                                                   // 'velocity all zero linear'
+  vcm[0] = s[0] / (m * N); vcm[1] = s[1] / (m * N); vcm[2] = s[2] / (m * N);
+  double xc[3] = { 0, 0, 0 };
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    cx.gv[i] -= vcm[0]; cx.gv[Npad + i] -= vcm[1]; cx.gv[2 * Npad + i] -= vcm[2];
+    xc[0] += m * cx.sx[i]; xc[1] += m * cx.sy[i]; xc[2] += m * cx.sz[i];
+  }
+  block_sum<3>(xc, cx.red);                                                  // 'velocity all zero angular'
+  xc[0] /= (m * N); xc[1] /= (m * N); xc[2] /= (m * N);
+  double a[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // L(3), Ixx Iyy Izz Ixy Iyz Ixz
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double dx = cx.sx[i] - xc[0], dy = cx.sy[i] - xc[1], dz = cx.sz[i] - xc[2];
+    const double vx = cx.gv[i], vy = cx.gv[Npad + i], vz = cx.gv[2 * Npad + i];
+    a[0] += m * (dy * vz - dz * vy); a[1] += m * (dz * vx - dx * vz); a[2] += m * (dx * vy - dy * vx);
+    a[3] += m * (dy * dy + dz * dz); a[4] += m * (dx * dx + dz * dz); a[5] += m * (dx * dx + dy * dy);
+    a[6] -= m * dx * dy; a[7] -= m * dy * dz; a[8] -= m * dx * dz;
+  }
+  block_sum<9>(a, cx.red);
+  const double I00 = a[3], I11 = a[4], I22 = a[5], I01 = a[6], I12 = a[7], I02 = a[8];
+  const double det = I00 * (I11 * I22 - I12 * I12) - I01 * (I01 * I22 - I12 * I02) + I02 * (I01 * I12 - I11 * I02);
+  double w0 = 0, w1 = 0, w2 = 0;
+  if (det > 0.0) {
+    const double i00 = (I11 * I22 - I12 * I12) / det, i01 = -(I01 * I22 - I02 * I12) / det, i02 = (I01 * I12 - I02 * I11) / det;
+    const double i11 = (I00 * I22 - I02 * I02) / det, i12 = -(I00 * I12 - I02 * I01) / det, i22 = (I00 * I11 - I01 * I01) / det;
+    w0 = i00 * a[0] + i01 * a[1] + i02 * a[2];
+    w1 = i01 * a[0] + i11 * a[1] + i12 * a[2];
+    w2 = i02 * a[0] + i12 * a[1] + i22 * a[2];
+  }
+  t[0] = 0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double dx = cx.sx[i] - xc[0], dy = cx.sy[i] - xc[1], dz = cx.sz[i] - xc[2];
+    const double vx = cx.gv[i] - (w1 * dz - w2 * dy), vy = cx.gv[Npad + i] - (w2 * dx - w0 * dz), vz = cx.gv[2 * Npad + i] - (w0 * dy - w1 * dx);
+    cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+    t[0] += vx * vx + vy * vy + vz * vz;
+  }
+  block_sum<1>(t, cx.red);
+  return 0.5 * m * t[0];
+}
+
+// ------------------------------------------------------------------ a-3 / a-5 hamiltonian_mc (lammps_remcmc.py:598-640)
+__device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double t_vel, double dts, Energy& en, double* cnt) {
+  const int N = cx.N, Npad = cx.Npad;
+  const double ke0 = velocity_create(d, cx, r, t_vel);
+  save_xf(cx, true);
+  const double dt = d.text_rounding ? round6(dts) : dts;                        // 'timestep %f'
+  const double dtf = 0.5 * dt / d.mass;
+  const double etot = en.pe / et + ke0 / et;
+  double o[4] = { 0, 0, 0, 0 };
+  for (int st = 0; st < d.nstps; st++) {
+    const double invL = 1.0 / cx.L;
+    int flag = cx.thr2 < 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double vx = fma(dtf, cx.gf[i], cx.gv[i]), vy = fma(dtf, cx.gf[Npad + i], cx.gv[Npad + i]),
+                   vz = fma(dtf, cx.gf[2 * Npad + i], cx.gv[2 * Npad + i]);
+      cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+      const double x = wrap1(fma(dt, vx, cx.sx[i]), cx.L), y = wrap1(fma(dt, vy, cx.sy[i]), cx.L), z = wrap1(fma(dt, vz, cx.sz[i]), cx.L);
+      cx.sx[i] = x; cx.sy[i] = y; cx.sz[i] = z;
+      if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
+    }
+    sync_and_maybe_build(d, cx, flag);
+    if (st == d.nstps - 1) eval_forces<true, true>(d, cx, dtf, o);
+    else eval_forces<false, true>(d, cx, dtf, o);
+  }
+  bool acc = false;
+  if (threadIdx.x == 0) {
+    const double etotnew = o[0] / et + o[3] / et;
+    acc = metropolis(etotnew - etot, r, 0, P_HMC_ACC);
+    cnt[4] += 1.0; if (acc) cnt[5] += 1.0;
+    cx.ct[NM_CT_HMC_MOVES]++; cx.ct[NM_CT_HMC_ATOM_STEPS] += (unsigned long long)N * d.nstps;
+  }
+  acc = broadcast_flag(cx, acc);
+  if (acc) { en.pe = o[0]; en.w = o[1]; } else restore_xf(cx, true);
+}
+
+// ------------------------------------------------------------------ a-8 iter_position_mc (lammps_remcmc.py:505-549)
+// The reference re-evaluates the whole system for each of the N sequential single-atom trials; here warp 0
+// walks the same sequential chain with the single-atom energy change summed over the atom's list column.
+__device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double dxs, Energy& en, double* cnt) {
+  const int N = cx.N, Npad = cx.Npad, lane = threadIdx.x & 31;
+  const double rc = d.rc, rc2 = rc * rc, rl = rc + d.skin, L = cx.L, hL = 0.5 * L, invL = 1.0 / L;
+  check_list(d, cx);
+  // umax: largest displacement (build units) of any atom from its list reference
+  double um[1] = { 0.0 };
+  {
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmax(mx, disp2(cx, i, cx.sx[i], cx.sy[i], cx.sz[i], invL));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if (lane == 0) cx.red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) { double q = 0.0; for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) q = fmax(q, cx.red[w]); cx.bc[8] = sqrt(q); }
+    __syncthreads();
+    um[0] = cx.bc[8];
+  }
+  int k = 0;
+  unsigned long long ntrial = 0, nacc = 0, nvis = 0;
+  while (k < N) {
+    if (threadIdx.x < 32) {
+      double umax = um[0];
+      const double s = L / cx.L0;
+      int kk = k, need = 0;
+      for (; kk < N; kk++) {
+        double u[3]; rng_uniform3(r, (uint32_t)kk, P_ITER_DISP, u);
+        const double xo = cx.sx[kk], yo = cx.sy[kk], zo = cx.sz[kk];
+        double xn = xo + 2 * (u[0] - 0.5) * dxs * d.lat, yn = yo + 2 * (u[1] - 0.5) * dxs * d.lat, zn = zo + 2 * (u[2] - 0.5) * dxs * d.lat;
+        xn -= floor(xn / L) * L; yn -= floor(yn / L) * L; zn -= floor(zn / L) * L;
+        xn = wrap1(xn, L); yn = wrap1(yn, L); zn = wrap1(zn, L);
+        const double un = sqrt(disp2(cx, kk, xn, yn, zn, invL));
+        // every atom within rc of the old or the new position must be in column kk of the list
+        const bool list_ok = s * (rl - un - umax) >= rc * (1 + 1e-9) && s * (rl - 2.0 * umax) >= rc * (1 + 1e-9);
+        bool brute = false;
+        if (!list_ok) {
+          const double ddx = mic_exact(xn - xo, L, hL), ddy = mic_exact(yn - yo, L, hL), ddz = mic_exact(zn - zo, L, hL);
+          const double step = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+          if (rl - step >= rc * (1 + 1e-9)) { need = 1; break; }   // a fresh list would do: rebuild, then retry kk
+          brute = true;                                            // step larger than the skin: all-atom sum
+        }
+        double de = 0.0; int vis = 0;
+        auto pair = [&](int j) {
+          const double ax = mic_exact(xn - cx.sx[j], L, hL), ay = mic_exact(yn - cx.sy[j], L, hL), az = mic_exact(zn - cx.sz[j], L, hL);
+          const double bx = mic_exact(xo - cx.sx[j], L, hL), by = mic_exact(yo - cx.sy[j], L, hL), bz = mic_exact(zo - cx.sz[j], L, hL);
+          const double rn = ax * ax + ay * ay + az * az, ro = bx * bx + by * by + bz * bz;
+          if (rn < rc2) { const double r2 = 1.0 / rn, r6 = r2 * r2 * r2; de += r6 * (4.0 * r6 - 4.0); vis++; }
+          if (ro < rc2) { const double r2 = 1.0 / ro, r6 = r2 * r2 * r2; de -= r6 * (4.0 * r6 - 4.0); vis++; }
+        };
+        if (brute) {
+          for (int j = lane; j < N; j += 32) if (j != kk) pair(j);
+        } else {
+          const int nq = (cx.nnb[kk] + 3) >> 2;
+          for (int q = lane; q < nq; q += 32) {
+            const ushort4 e4 = cx.list[(size_t)q * Npad + kk];
+            pair(e4.x); pair(e4.y); pair(e4.z); pair(e4.w);
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) { de += __shfl_xor_sync(0xffffffffu, de, o); vis += __shfl_xor_sync(0xffffffffu, vis, o); }
+        const bool acc = metropolis(de / et, r, (uint32_t)kk, P_ITER_ACC);
+        ntrial++; nvis += vis;
+        if (acc) {
+          nacc++; en.pe += de;
+          __syncwarp();
+          if (lane == 0) { cx.sx[kk] = xn; cx.sy[kk] = yn; cx.sz[kk] = zn; }
+          __syncwarp();
+          umax = fmax(umax, un);
+        }
+      }
+      if (lane == 0) { cx.ibc[1] = kk; cx.ibc[2] = need; cx.bc[8] = umax; }
+    }
+    __syncthreads();
+    k = cx.ibc[1];
+    const int need = cx.ibc[2];
+    um[0] = cx.bc[8];
+    __syncthreads();
+    if (need) { build_list(d, cx); um[0] = 0.0; }
+  }
+  if (threadIdx.x == 0) {
+    cnt[0] += (double)ntrial; cnt[1] += (double)nacc;
+    cx.ct[NM_CT_PMC_MOVES]++; cx.ct[NM_CT_PMC_TRIALS] += ntrial; cx.ct[NM_CT_PAIRS_DELTA] += nvis;
+  }
+  // the state the last 'run 0' of the sweep leaves: a fresh full evaluation
+  check_list(d, cx);
+  double o[4]; eval_forces<true, false>(d, cx, 0.0, o);
+  en.pe = o[0]; en.w = o[1];
+}
+
+// ------------------------------------------------------------------ kernels
+// 'run 0' on the resident configurations: wrap, (re)build list, evaluate; optionally export.
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
+k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npairs_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx cx; ctx_init(d, cx, blockIdx.x, smem);
+  if (cx.L < 2.0 * d.rc * (1.0 + 1e-5)) { if (threadIdx.x == 0) d.status[cx.c] |= ST_BOX; return; }
+  load_positions(d, cx);
+  update_thr(d, cx);
+  __syncthreads();
+  check_list(d, cx);
+  double o[4]; eval_forces<true, false>(d, cx, 0.0, o);
+  store_positions(cx);
+  double t[1] = { 0 };
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+    const double vx = cx.gv[i], vy = cx.gv[cx.Npad + i], vz = cx.gv[2 * cx.Npad + i];
+    t[0] += vx * vx + vy * vy + vz * vz;
+  }
+  block_sum<1>(t, cx.red);
+  const int slot = d.cfg_slot[cx.c];
+  if (f_out_aos) {
+    double* fo = f_out_aos + (size_t)slot * 3 * cx.N;
+    for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+      fo[3 * i] = cx.gf[i]; fo[3 * i + 1] = cx.gf[cx.Npad + i]; fo[3 * i + 2] = cx.gf[2 * cx.Npad + i];
+    }
+  }
+  if (threadIdx.x == 0) {
+    d.pe[cx.c] = o[0]; d.w[cx.c] = o[1]; d.ke[cx.c] = 0.5 * d.mass * t[0]; d.L0[cx.c] = cx.L0; d.list_pairs[cx.c] = cx.list_pairs;
+    if (pe_out) pe_out[slot] = o[0];
+    if (w_out) w_out[slot] = o[1];
+    if (npairs_out) npairs_out[slot] = (long long)o[2];
+    if (cx.status) d.status[cx.c] |= cx.status;
+    for (int k = 0; k < NM_COUNTER_WIDTH; k++) if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]);
+  }
+}
+
+// gen_sample (lammps_remcmc.py:665-691): MOD x move_mc (:643-658), then lammps_extract (:377-391)
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
+k_cycle(Dev d, long long cycle) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx cx; ctx_init(d, cx, blockIdx.x, smem);
+  const int c = cx.c, slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
+  const double et = d.label[4 * slot], pf = d.label[4 * slot + 1], t_vel = d.label[4 * slot + 3];
+  const double dxs = d.step[3 * c], dvs = d.step[3 * c + 1], dts = d.step[3 * c + 2];
+  load_positions(d, cx);
+  update_thr(d, cx);
+  Energy en = { d.pe[c], d.w[c] };
+  double cnt[6];
+  for (int k = 0; k < 6; k++) cnt[k] = d.cnt[6 * c + k];
+  __syncthreads();
+  for (int mv = 0; mv < d.mod; mv++) {
+    const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)(d.rep_offset + slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
+    const double roll = rng_uniform(r, 0, P_ROLL);
+    if (roll <= d.ppos) {
+      if (d.bulk) bulk_position_mc(d, cx, r, et, dxs, en, cnt);
+      else iter_position_mc(d, cx, r, et, dxs, en, cnt);
+    } else if (roll <= (d.ppos + d.pvol)) volume_mc(d, cx, r, et, pf, dvs, en, cnt);
+    else hamiltonian_mc(d, cx, r, et, t_vel, dts, en, cnt);
+    if (threadIdx.x == 0) cx.ct[NM_CT_SWEEPS]++;
+  }
+  // lammps_extract
+  double t[1] = { 0 };
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double vx = cx.gv[i], vy = cx.gv[Npad + i], vz = cx.gv[2 * Npad + i];
+    t[0] += vx * vx + vy * vy + vz * vz;
+  }
+  block_sum<1>(t, cx.red);
+  store_positions(cx);
+  if (threadIdx.x == 0) {
+    const double ke = 0.5 * d.mass * t[0], dof = 3.0 * N - 3.0, temp = 2.0 * ke / dof, vol = pow(cx.L, 3.0);
+    double* th = d.thermo + (size_t)slot * NM_THERMO_WIDTH;
+    th[NM_TH_TEMP] = temp; th[NM_TH_PE] = en.pe; th[NM_TH_KE] = ke;
+    th[NM_TH_VIRIAL] = (dof * temp + en.w) / 3.0 * (1.0 / vol);
+    th[NM_TH_BOX] = cx.L; th[NM_TH_VOL] = vol; th[NM_TH_DX] = dxs; th[NM_TH_DV] = dvs; th[NM_TH_DT] = dts;
+    for (int k = 0; k < 6; k++) { th[NM_TH_NTP + k] = cnt[k]; d.cnt[6 * c + k] = cnt[k]; }
+    for (int k = 0; k < 3; k++) {
+      const float a = (float)cnt[2 * k + 1] / (float)cnt[2 * k];        // float32 ratio, nan_to_num (0/0 -> 0)
+      th[NM_TH_AP + k] = isnan(a) ? 0.0 : (double)a;
+    }
+    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.list_pairs[c] = cx.list_pairs;
+    if (cx.status) d.status[c] |= cx.status;
+    cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
+    for (int k = 0; k < NM_COUNTER_WIDTH; k++) if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]);
+  }
+}
+
+// gen_mc_param (lammps_remcmc.py:726-745): ratios are the float32 values stored in the thermo record
+__global__ void k_adapt(Dev d) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d.nrep) return;
+  const int c = d.slot_cfg[k];
+  const double* th = d.thermo + (size_t)k * NM_THERMO_WIDTH;
+  for (int a = 0; a < 3; a++) {
+    const double ratio = th[NM_TH_AP + a];
+    double s = d.step[3 * c + a];
+    if (ratio < 0.5) s = 0.9375 * s;
+    if (ratio > 0.5) s = 1.0625 * s;
+    d.step[3 * c + a] = s;
+  }
+  for (int a = 0; a < 6; a++) d.cnt[6 * c + a] = 0.0;
+}
+
+// exchange payload: (pe + ke, vol) per local slot, as lammps_remcmc.py:791 reads them from STATE
+__global__ void k_exchange_pack(Dev d, double* dst) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d.nrep) return;
+  const int c = d.slot_cfg[k];
+  dst[2 * k] = d.pe[c] + d.ke[c];
+  dst[2 * k + 1] = pow(d.box[c], 3.0);
+}
+
+// replica_exchange (lammps_remcmc.py:776-803): one thread replays the sequential sweep of one pressure row.
+// table: [ns][2] by slot (copied to scratch e/v so swaps are seen by later pairs), perm[k] = source slot of slot k.
+__global__ void k_exchange_sweep(int np_, int nt, const double* table, const double* et, const double* pf,
+                                 const double* uniforms, uint32_t seed_lo, uint32_t seed_hi, long long cycle,
+                                 double* scratch, int* perm, unsigned long long* swaps) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= np_) return;
+  const int ns = np_ * nt;
+  double* e = scratch; double* vv = scratch + ns;
+  for (int t = 0; t < nt; t++) { const int k = u * nt + t; e[k] = table[2 * k]; vv[k] = table[2 * k + 1]; perm[k] = k; }
+  unsigned long long draw = (unsigned long long)u * (unsigned long long)(nt * (nt - 1) / 2), sw = 0;
+  for (int v = nt - 1; v >= 0; v--)
+    for (int w = 0; w < v; w++) {
+      const int i = u * nt + v, j = u * nt + w;
+      const double de = e[i] - e[j], dvol = vv[i] - vv[j];
+      const double dh = de * (1. / et[i] - 1. / et[j]) + (pf[i] - pf[j]) * dvol;
+      const double m = exp(dh), crit = isnan(m) ? m : (m < 1.0 ? m : 1.0);
+      double un;
+      if (uniforms) un = uniforms[draw];
+      else {
+        uint32_t wd[4];
+        philox4x32_10(seed_lo, seed_hi ^ NM_EXCH_KEY, (uint32_t)draw, P_EXCH, (uint32_t)cycle, (uint32_t)((unsigned long long)cycle >> 32), wd);
+        un = u53(wd[0], wd[1]);
+      }
+      draw++;
+      if (un <= crit) {
+        sw++;
+        double t = e[i]; e[i] = e[j]; e[j] = t; t = vv[i]; vv[i] = vv[j]; vv[j] = t;
+        int q = perm[i]; perm[i] = perm[j]; perm[j] = q;
+      }
+    }
+  atomicAdd(swaps, sw);
+}
+// apply the (row-local) permutation to the local slot -> configuration labels
+__global__ void k_exchange_permute(Dev d, const int* perm_global, int* tmp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < d.nrep) tmp[k] = d.slot_cfg[perm_global[d.rep_offset + k] - d.rep_offset];
+}
+__global__ void k_exchange_commit(Dev d, const int* tmp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < d.nrep) { d.slot_cfg[k] = tmp[k]; d.cfg_slot[tmp[k]] = k; }
+}
+
+// host AoS (slot order) <-> device SoA (configuration order)
+__global__ void k_scatter_state(Dev d, const double* x_aos, const double* v_aos, const double* box,
+                                const double* dx, const double* dv, const double* dt) {
+  const int k = blockIdx.x, c = d.slot_cfg[k], N = d.N, Npad = d.Npad;
+  const size_t off = (size_t)c * 3 * Npad;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    for (int a = 0; a < 3; a++) {
+      if (x_aos) d.x[off + a * Npad + i] = x_aos[((size_t)k * N + i) * 3 + a];
+      if (v_aos) d.v[off + a * Npad + i] = v_aos[((size_t)k * N + i) * 3 + a];
+    }
+  if (threadIdx.x == 0) {
+    if (box) d.box[c] = box[k];
+    if (dx) d.step[3 * c] = dx[k];
+    if (dv) d.step[3 * c + 1] = dv[k];
+    if (dt) d.step[3 * c + 2] = dt[k];
+    if (x_aos || box) d.L0[c] = -1.0;      // new configuration: the old list is meaningless
+  }
+}
+__global__ void k_gather_state(Dev d, double* x_aos, double* v_aos, double* box, double* dx, double* dv, double* dt) {
+  const int k = blockIdx.x, c = d.slot_cfg[k], N = d.N, Npad = d.Npad;
+  const size_t off = (size_t)c * 3 * Npad;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    for (int a = 0; a < 3; a++) {
+      if (x_aos) x_aos[((size_t)k * N + i) * 3 + a] = d.x[off + a * Npad + i];
+      if (v_aos) v_aos[((size_t)k * N + i) * 3 + a] = d.v[off + a * Npad + i];
+    }
+  if (threadIdx.x == 0) {
+    if (box) box[k] = d.box[c];
+    if (dx) dx[k] = d.step[3 * c];
+    if (dv) dv[k] = d.step[3 * c + 1];
+    if (dt) dt[k] = d.step[3 * c + 2];
+  }
+}
+
+}  // namespace nm
+
+// =================================================================== host side / C-ABI
+using namespace nm;
+
+static thread_local char g_err[512] = "";
+// shared by every translation unit of the library (not part of the C-ABI)
+int nm_fail_msg(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+#define fail nm_fail_msg
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(NM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct nm_engine {
+  nm_config cfg;
+  Dev d;
+  cudaStream_t stream; bool own_stream;
+  int threads; size_t smem;
+  std::vector<void*> allocs;
+  double *stage_a, *stage_b, *stage_s;     // device staging: x/v AoS [nrep][3N], scalars [nrep][8]
+  double *ex_table, *ex_et, *ex_pf, *ex_uni, *ex_scratch; int *ex_perm, *ex_tmp; unsigned long long* ex_swaps;
+  long long* np_out;
+  bool have_state, have_labels, have_thermo;
+  int64_t launches;
+};
+
+template <typename T>
+static int dev_alloc(nm_engine* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) return fail(NM_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  e = cudaMemset(q, 0, n * sizeof(T));
+  if (e != cudaSuccess) return fail(NM_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  h->allocs.push_back(q); *p = static_cast<T*>(q);
+  return NM_OK;
+}
+#define DA(ptr, n) do { int r_ = dev_alloc(h, &(ptr), (n)); if (r_) { nm_destroy(h); return r_; } } while (0)
+
+extern "C" {
+
+const char* nm_last_error(void) { return g_err; }
+int nm_abi_version(void) { return NM_ABI_VERSION; }
+int nm_device_count(void) {
+  int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(NM_ENODEV, "no CUDA device: %s", cudaGetErrorString(e)); }
+  return n;
+}
+
+int nm_create(const nm_config* cfg, nm_engine** out) {
+  if (!cfg || !out) return fail(NM_EINVAL, "nm_create: null argument");
+  if (cfg->struct_size != (int32_t)sizeof(nm_config)) return fail(NM_EINVAL, "nm_create: nm_config size mismatch (%d vs %zu)", cfg->struct_size, sizeof(nm_config));
+  if (cfg->natoms < 2 || cfg->natoms > 65000) return fail(NM_EINVAL, "nm_create: natoms %d out of range [2, 65000]", cfg->natoms);
+  if (cfg->n_rep < 1 || cfg->nt < 1 || cfg->n_rep % cfg->nt || cfg->rep_offset % cfg->nt || cfg->n_rep_global < cfg->rep_offset + cfg->n_rep)
+    return fail(NM_EINVAL, "nm_create: local slots must be whole pressure rows (n_rep=%d rep_offset=%d nt=%d global=%d)", cfg->n_rep, cfg->rep_offset, cfg->nt, cfg->n_rep_global);
+  if (cfg->precision != 64 && cfg->precision != 0) return fail(NM_EINVAL, "nm_create: precision %d not available in this build (64 only)", cfg->precision);
+  if (cfg->nstps < 1 || cfg->mod < 0 || cfg->ppos < 0 || cfg->pvol < 0 || cfg->ppos + cfg->pvol > 1.0 + 1e-12) return fail(NM_EINVAL, "nm_create: bad move parameters");
+  if (!(cfg->rc > 0) || !(cfg->mass > 0)) return fail(NM_EINVAL, "nm_create: rc and mass must be positive");
+  int ndev = nm_device_count();
+  if (ndev < 0) return ndev;
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(NM_ENODEV, "nm_create: device %d not in [0,%d)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  nm_engine* h = new (std::nothrow) nm_engine();
+  if (!h) return fail(NM_ENOMEM, "nm_create: host allocation failed");
+  h->cfg = *cfg;
+  h->own_stream = cfg->stream == nullptr;
+  if (h->own_stream) { cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { delete h; return fail(NM_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); } }
+  else h->stream = (cudaStream_t)cfg->stream;
+  Dev& d = h->d;
+  memset(&d, 0, sizeof d);
+  const int N = cfg->natoms, nrep = cfg->n_rep;
+  d.N = N; d.Npad = ((N + 1) + 31) & ~31; d.nrep = nrep; d.nrep_global = cfg->n_rep_global; d.rep_offset = cfg->rep_offset; d.nt = cfg->nt;
+  d.nstps = cfg->nstps; d.mod = cfg->mod; d.bulk = cfg->bulk_move; d.text_rounding = cfg->text_rounding;
+  d.ppos = cfg->ppos; d.pvol = cfg->pvol; d.lat = cfg->lat_scale; d.mass = cfg->mass; d.rc = cfg->rc;
+  d.skin = cfg->skin > 0 ? cfg->skin : 0.3;
+  d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);
+  {
+    // list capacity: neighbours inside rc+skin at the densest state we expect (rho* 1.6) plus slack
+    const double rl = d.rc + d.skin;
+    int maxnb = (int)(4.18879 * rl * rl * rl * 1.6) + 16;
+    if (maxnb > N - 1) maxnb = N - 1;
+    d.maxq = (maxnb + 3) / 4; if (d.maxq < 1) d.maxq = 1;
+  }
+  h->threads = N <= 256 ? 256 : 512;     // 512 threads keep the cycle kernel at 128 registers without spills
+  h->smem = smem_bytes(d.Npad);
+  if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
+  const size_t per = (size_t)nrep * 3 * d.Npad;
+  DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, per);
+  DA(d.list, (size_t)nrep * d.maxq * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad);
+  DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
+  DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
+  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep);
+  DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
+  DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
+  const int nsg = cfg->n_rep_global;
+  DA(h->ex_table, 2 * (size_t)nsg); DA(h->ex_et, nsg); DA(h->ex_pf, nsg); DA(h->ex_uni, (size_t)nsg * cfg->nt); DA(h->ex_scratch, 2 * (size_t)nsg);
+  DA(h->ex_perm, nsg); DA(h->ex_tmp, nrep); DA(h->ex_swaps, 1); DA(h->np_out, nrep);
+  {
+    std::vector<int> id(nrep); for (int k = 0; k < nrep; k++) id[k] = k;
+    std::vector<double> neg(nrep, -1.0);
+    cudaError_t e1 = cudaMemcpy(d.cfg_slot, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
+    cudaError_t e2 = cudaMemcpy(d.slot_cfg, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
+    cudaError_t e3 = cudaMemcpy(d.L0, neg.data(), sizeof(double) * nrep, cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "nm_create: init copy failed"); }
+  }
+  cudaError_t e = cudaSuccess;
+  const int sm = (int)h->smem;
+  if (h->threads == 256) { e = cudaFuncSetAttribute(k_cycle<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
+  else { e = cudaFuncSetAttribute(k_cycle<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
+  if (e != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "cudaFuncSetAttribute(smem=%zu): %s", h->smem, cudaGetErrorString(e)); }
+  *out = h;
+  return NM_OK;
+}
+
+int nm_destroy(nm_engine* h) {
+  if (!h) return NM_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return NM_OK;
+}
+
+int nm_set_stream(nm_engine* h, void* s) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->own_stream) { cudaStreamDestroy(h->stream); h->own_stream = false; }
+  h->stream = (cudaStream_t)s;
+  return NM_OK;
+}
+int nm_synchronize(nm_engine* h) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  return NM_OK;
+}
+
+static int check_status(nm_engine* h) {
+  std::vector<int> st(h->d.nrep);
+  CK(cudaMemcpyAsync(st.data(), h->d.status, sizeof(int) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < h->d.nrep; c++) {
+    if (st[c] & ST_BOX) return fail(NM_EBOX, "configuration %d: box side below 2*rc (minimum image invalid)", c);
+    if (st[c] & ST_NEIGH) return fail(NM_ENEIGH, "configuration %d: neighbour list capacity (%d) exceeded", c, h->d.maxq * 4);
+  }
+  return NM_OK;
+}
+
+static int launch_eval(nm_engine* h, double* pe, double* w, double* f_aos, long long* np_) {
+  if (h->threads == 256) k_eval<256><<<h->d.nrep, 256, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
+  else k_eval<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
+  h->launches++;
+  CK(cudaGetLastError());
+  return NM_OK;
+}
+
+int nm_set_state(nm_engine* h, const double* x, const double* v, const double* box,
+                 const double* dx, const double* dv, const double* dt) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  CK(cudaSetDevice(h->cfg.device));
+  const int nrep = h->d.nrep; const size_t n3 = (size_t)nrep * 3 * h->d.N;
+  if (!h->have_state && (!x || !box)) return fail(NM_ESTATE, "nm_set_state: the first upload needs positions and box");
+  if (x) CK(cudaMemcpyAsync(h->stage_a, x, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
+  if (v) CK(cudaMemcpyAsync(h->stage_b, v, sizeof(double) * n3, cudaMemcpyHostToDevice, h->stream));
+  const double* src[4] = { box, dx, dv, dt };
+  for (int q = 0; q < 4; q++) if (src[q]) CK(cudaMemcpyAsync(h->stage_s + (size_t)q * nrep, src[q], sizeof(double) * nrep, cudaMemcpyHostToDevice, h->stream));
+  k_scatter_state<<<nrep, 256, 0, h->stream>>>(h->d, x ? h->stage_a : nullptr, v ? h->stage_b : nullptr,
+      box ? h->stage_s : nullptr, dx ? h->stage_s + nrep : nullptr, dv ? h->stage_s + 2 * nrep : nullptr, dt ? h->stage_s + 3 * nrep : nullptr);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->have_state = true;
+  if (x || box) {                       // the 'run 0' of init_lammps
+    int r = launch_eval(h, nullptr, nullptr, nullptr, nullptr); if (r) return r;
+    return check_status(h);
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return NM_OK;
+}
+
+int nm_get_state(nm_engine* h, double* x, double* v, double* box, double* dx, double* dv, double* dt) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  if (!h->have_state) return fail(NM_ESTATE, "nm_get_state: no state uploaded");
+  CK(cudaSetDevice(h->cfg.device));
+  const int nrep = h->d.nrep; const size_t n3 = (size_t)nrep * 3 * h->d.N;
+  k_gather_state<<<nrep, 256, 0, h->stream>>>(h->d, x ? h->stage_a : nullptr, v ? h->stage_b : nullptr,
+      h->stage_s, h->stage_s + nrep, h->stage_s + 2 * nrep, h->stage_s + 3 * nrep);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (x) CK(cudaMemcpyAsync(x, h->stage_a, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+  if (v) CK(cudaMemcpyAsync(v, h->stage_b, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+  double* dst[4] = { box, dx, dv, dt };
+  for (int q = 0; q < 4; q++) if (dst[q]) CK(cudaMemcpyAsync(dst[q], h->stage_s + (size_t)q * nrep, sizeof(double) * nrep, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return NM_OK;
+}
+
+int nm_set_labels(nm_engine* h, const double* et, const double* pf, const double* temp, const double* temp_vel) {
+  if (!h || !et || !pf || !temp || !temp_vel) return fail(NM_EINVAL, "nm_set_labels: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<double> lab(4 * (size_t)h->d.nrep);
+  for (int k = 0; k < h->d.nrep; k++) {
+    if (!(et[k] > 0)) return fail(NM_EINVAL, "nm_set_labels: et[%d] must be positive", k);
+    lab[4 * k] = et[k]; lab[4 * k + 1] = pf[k]; lab[4 * k + 2] = temp[k]; lab[4 * k + 3] = temp_vel[k];
+  }
+  CK(cudaMemcpyAsync(h->d.label, lab.data(), sizeof(double) * lab.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_labels = true;
+  return NM_OK;
+}
+
+int nm_eval(nm_engine* h, double* pe, double* w, double* f, int64_t* npairs) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  if (!h->have_state) return fail(NM_ESTATE, "nm_eval: no state uploaded");
+  CK(cudaSetDevice(h->cfg.device));
+  const int nrep = h->d.nrep; const size_t n3 = (size_t)nrep * 3 * h->d.N;
+  int r = launch_eval(h, h->stage_s, h->stage_s + nrep, f ? h->stage_a : nullptr, h->np_out); if (r) return r;
+  if (pe) CK(cudaMemcpyAsync(pe, h->stage_s, sizeof(double) * nrep, cudaMemcpyDeviceToHost, h->stream));
+  if (w) CK(cudaMemcpyAsync(w, h->stage_s + nrep, sizeof(double) * nrep, cudaMemcpyDeviceToHost, h->stream));
+  if (f) CK(cudaMemcpyAsync(f, h->stage_a, sizeof(double) * n3, cudaMemcpyDeviceToHost, h->stream));
+  if (npairs) CK(cudaMemcpyAsync(npairs, h->np_out, sizeof(long long) * nrep, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+int nm_run_cycle(nm_engine* h, int64_t cycle) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  if (!h->have_state || !h->have_labels) return fail(NM_ESTATE, "nm_run_cycle: state and labels must be uploaded first");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->threads == 256) k_cycle<256><<<h->d.nrep, 256, h->smem, h->stream>>>(h->d, (long long)cycle);
+  else k_cycle<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, (long long)cycle);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->have_thermo = true;
+  return NM_OK;
+}
+
+int nm_get_thermo(nm_engine* h, double* out) {
+  if (!h || !out) return fail(NM_EINVAL, "nm_get_thermo: null argument");
+  if (!h->have_thermo) return fail(NM_ESTATE, "nm_get_thermo: no cycle has run");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(out, h->d.thermo, sizeof(double) * (size_t)h->d.nrep * NM_THERMO_WIDTH, cudaMemcpyDeviceToHost, h->stream));
+  return check_status(h);
+}
+
+int nm_adapt(nm_engine* h) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  if (!h->have_thermo) return fail(NM_ESTATE, "nm_adapt: no cycle has run");
+  CK(cudaSetDevice(h->cfg.device));
+  k_adapt<<<(h->d.nrep + 127) / 128, 128, 0, h->stream>>>(h->d);
+  h->launches++;
+  CK(cudaGetLastError());
+  return NM_OK;
+}
+
+int nm_exchange_pack(nm_engine* h, void* dev_dst) {
+  if (!h || !dev_dst) return fail(NM_EINVAL, "nm_exchange_pack: null argument");
+  if (!h->have_state) return fail(NM_ESTATE, "nm_exchange_pack: no state uploaded");
+  CK(cudaSetDevice(h->cfg.device));
+  k_exchange_pack<<<(h->d.nrep + 127) / 128, 128, 0, h->stream>>>(h->d, (double*)dev_dst);
+  h->launches++;
+  CK(cudaGetLastError());
+  return NM_OK;
+}
+
+int nm_exchange_apply(nm_engine* h, const void* dev_table_global, const double* et_global, const double* pf_global,
+                      const double* uniforms, int64_t cycle, int32_t* perm_out, int64_t* swaps_out) {
+  if (!h || !dev_table_global || !et_global || !pf_global) return fail(NM_EINVAL, "nm_exchange_apply: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const int ns = h->d.nrep_global, nt = h->d.nt, np_ = ns / nt;
+  CK(cudaMemcpyAsync(h->ex_et, et_global, sizeof(double) * ns, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->ex_pf, pf_global, sizeof(double) * ns, cudaMemcpyHostToDevice, h->stream));
+  const size_t nu = (size_t)np_ * nt * (nt - 1) / 2;
+  if (uniforms && nu) CK(cudaMemcpyAsync(h->ex_uni, uniforms, sizeof(double) * nu, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->ex_swaps, 0, sizeof(unsigned long long), h->stream));
+  k_exchange_sweep<<<(np_ + 31) / 32, 32, 0, h->stream>>>(np_, nt, (const double*)dev_table_global, h->ex_et, h->ex_pf,
+      uniforms ? h->ex_uni : nullptr, h->d.seed_lo, h->d.seed_hi, (long long)cycle, h->ex_scratch, h->ex_perm, h->ex_swaps);
+  k_exchange_permute<<<(h->d.nrep + 127) / 128, 128, 0, h->stream>>>(h->d, h->ex_perm, h->ex_tmp);
+  k_exchange_commit<<<(h->d.nrep + 127) / 128, 128, 0, h->stream>>>(h->d, h->ex_tmp);
+  h->launches += 3;
+  CK(cudaGetLastError());
+  if (perm_out || swaps_out) {
+    unsigned long long sw = 0;
+    if (perm_out) CK(cudaMemcpyAsync(perm_out, h->ex_perm, sizeof(int) * ns, cudaMemcpyDeviceToHost, h->stream));
+    if (swaps_out) CK(cudaMemcpyAsync(&sw, h->ex_swaps, sizeof sw, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (swaps_out) *swaps_out = (int64_t)sw;
+  }
+  return NM_OK;
+}
+
+int nm_exchange(nm_engine* h, const double* uniforms, int64_t cycle, int32_t* perm_out, int64_t* swaps_out) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  if (h->d.nrep != h->d.nrep_global) return fail(NM_EINVAL, "nm_exchange: single-rank call on a sharded engine; use pack + all-gather + apply");
+  if (!h->have_labels) return fail(NM_ESTATE, "nm_exchange: labels not set");
+  int r = nm_exchange_pack(h, h->ex_table); if (r) return r;
+  std::vector<double> lab(4 * (size_t)h->d.nrep), et(h->d.nrep), pf(h->d.nrep);
+  CK(cudaMemcpyAsync(lab.data(), h->d.label, sizeof(double) * lab.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < h->d.nrep; k++) { et[k] = lab[4 * k]; pf[k] = lab[4 * k + 1]; }
+  return nm_exchange_apply(h, h->ex_table, et.data(), pf.data(), uniforms, cycle, perm_out, swaps_out);
+}
+
+int nm_get_counters(nm_engine* h, uint64_t* out) {
+  if (!h || !out) return fail(NM_EINVAL, "nm_get_counters: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(out, h->d.counters, sizeof(uint64_t) * NM_COUNTER_WIDTH, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return NM_OK;
+}
+int nm_reset_counters(nm_engine* h) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->d.counters, 0, sizeof(uint64_t) * NM_COUNTER_WIDTH, h->stream));
+  return NM_OK;
+}
+int64_t nm_launch_count(nm_engine* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

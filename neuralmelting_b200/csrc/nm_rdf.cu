@@ -1,0 +1,184 @@
+// nm_rdf.cu -- bit-exact radial-distribution histogram (calculate_rdf, lammps_distr.py:123-135).
+//
+// The reference forms, for each of the 27 image vectors s in {-1,0,1}^3 and every ordered pair
+// (a, b), the float32 distance d = sqrt((dx^2 + dy^2) + dz^2) with d* = pos_a - (pos_b + box*s),
+// every operation rounded separately (NumPy array passes), and np.histogram's it on float64
+// edges. This kernel visits every ordered pair once, keeps per dimension only the shifts that can
+// land inside the last edge (normally exactly one), forms those distances with the SAME float32
+// operation sequence (no FMA contraction), and bins them with float32 thresholds that are exactly
+// equivalent to the float64 edge comparisons. Thread-private histogram columns in shared memory
+// (no atomics, no bank conflicts); integer / FP32 ALU bound, HBM traffic is 12 N bytes per sample.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <vector>
+
+#include "nm_b200.h"
+
+namespace nmrdf {
+
+constexpr int T = 256;
+
+struct RdfParams {
+  const float* pos; const float* box; uint32_t* counts;
+  const float* thr;            // [nb] float32 lower thresholds: (double)d >= edge[k]  <=>  d >= thr[k]
+  int N, nb, a_chunk, private_hist;
+  float t_top, cut, inv_dr;    // d <= t_top <=> (double)d <= edge[nb-1]; prune |delta| > cut
+};
+
+__device__ __forceinline__ void count_one(float dx, float dy, float dz, const RdfParams& p, const float* sthr,
+                                          uint32_t* hist) {
+  const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  const float d = __fsqrt_rn(s2);
+  const float t0 = sthr[0];
+  if (d >= t0 && d <= p.t_top) {
+    int k = (int)((d - t0) * p.inv_dr);
+    k = max(0, min(k, p.nb - 1));
+    while (k > 0 && d < sthr[k]) k--;
+    while (k < p.nb - 1 && d >= sthr[k + 1]) k++;
+    if (k == p.nb - 1) k = p.nb - 2;                       // last bin is right-closed
+    if (p.private_hist) hist[k * T + threadIdx.x]++;
+    else atomicAdd(&hist[k], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(T) k_rdf(RdfParams p) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* ax = reinterpret_cast<float*>(sm);
+  float* ay = ax + p.a_chunk; float* az = ay + p.a_chunk;
+  float* sthr = az + p.a_chunk;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(sthr + p.nb);
+  const int s = blockIdx.y, a0 = blockIdx.x * p.a_chunk, na = min(p.N, a0 + p.a_chunk) - a0;
+  const float* ps = p.pos + (size_t)s * p.N * 3;
+  for (int a = threadIdx.x; a < na; a += T) { ax[a] = ps[3 * (a0 + a)]; ay[a] = ps[3 * (a0 + a) + 1]; az[a] = ps[3 * (a0 + a) + 2]; }
+  for (int k = threadIdx.x; k < p.nb; k += T) sthr[k] = p.thr[k];
+  const int nh = p.private_hist ? p.nb * T : p.nb;
+  for (int k = threadIdx.x; k < nh; k += T) hist[k] = 0u;
+  __syncthreads();
+  const float bx = p.box[s], nbx = __fmul_rn(bx, -1.0f), cut = p.cut;
+  for (int b = threadIdx.x; b < p.N; b += T) {
+    // the three images of atom b along each axis: pos_b + box*s, s = -1, 0, +1 (lammps_distr.py:130)
+    const float px = ps[3 * b], py = ps[3 * b + 1], pz = ps[3 * b + 2];
+    const float xm = __fadd_rn(px, nbx), xp = __fadd_rn(px, bx);
+    const float ym = __fadd_rn(py, nbx), yp = __fadd_rn(py, bx);
+    const float zm = __fadd_rn(pz, nbx), zp = __fadd_rn(pz, bx);
+    for (int a = 0; a < na; a++) {
+      const float qx = ax[a], qy = ay[a], qz = az[a];
+      const float dx0 = __fsub_rn(qx, px), dxm = __fsub_rn(qx, xm), dxp = __fsub_rn(qx, xp);
+      const float dy0 = __fsub_rn(qy, py), dym = __fsub_rn(qy, ym), dyp = __fsub_rn(qy, yp);
+      const float dz0 = __fsub_rn(qz, pz), dzm = __fsub_rn(qz, zm), dzp = __fsub_rn(qz, zp);
+      const bool x0 = fabsf(dx0) <= cut, xmk = fabsf(dxm) <= cut, xpk = fabsf(dxp) <= cut;
+      const bool y0 = fabsf(dy0) <= cut, ymk = fabsf(dym) <= cut, ypk = fabsf(dyp) <= cut;
+      const bool z0 = fabsf(dz0) <= cut, zmk = fabsf(dzm) <= cut, zpk = fabsf(dzp) <= cut;
+      const int cx = x0 + xmk + xpk, cy = y0 + ymk + ypk, cz = z0 + zmk + zpk;
+      if (cx == 0 || cy == 0 || cz == 0) continue;
+      if (cx == 1 && cy == 1 && cz == 1) {
+        const float dx = x0 ? dx0 : (xmk ? dxm : dxp), dy = y0 ? dy0 : (ymk ? dym : dyp), dz = z0 ? dz0 : (zmk ? dzm : dzp);
+        count_one(dx, dy, dz, p, sthr, hist);
+      } else {                                              // rare: an axis with two admissible images
+        const float vx[3] = { dxm, dx0, dxp }, vy[3] = { dym, dy0, dyp }, vz[3] = { dzm, dz0, dzp };
+        const bool kx[3] = { xmk, x0, xpk }, ky[3] = { ymk, y0, ypk }, kz[3] = { zmk, z0, zpk };
+        for (int i = 0; i < 3; i++) if (kx[i])
+          for (int j = 0; j < 3; j++) if (ky[j])
+            for (int k = 0; k < 3; k++) if (kz[k]) count_one(vx[i], vy[j], vz[k], p, sthr, hist);
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t* out = p.counts + (size_t)s * p.nb;
+  if (p.private_hist) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = wid; k < p.nb - 1; k += T / 32) {
+      uint32_t v = 0;
+      for (int j = lane; j < T; j += 32) v += hist[k * T + j];
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (lane == 0 && v) atomicAdd(&out[1 + k], v);
+    }
+  } else {
+    for (int k = threadIdx.x; k < p.nb - 1; k += T) if (hist[k]) atomicAdd(&out[1 + k], hist[k]);
+  }
+}
+
+}  // namespace nmrdf
+
+static thread_local char g_rdf_err[512] = "";
+extern "C" const char* nm_last_error(void);
+// error text is routed through the engine's thread-local buffer
+extern int nm_fail_msg(int code, const char* fmt, ...);
+
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = nm_fail_msg(NM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); goto done; } } while (0)
+
+extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const float* pos, const float* box,
+                             int32_t natoms, int64_t nsamples, const double* edges, int32_t nbins, uint32_t* counts) {
+  using namespace nmrdf;
+  if (!pos || !box || !edges || !counts) return nm_fail_msg(NM_EINVAL, "nm_rdf_counts: null argument");
+  if (natoms < 1 || nsamples < 0 || nbins < 2 || nbins > 4096) return nm_fail_msg(NM_EINVAL, "nm_rdf_counts: bad sizes (natoms=%d nsamples=%lld nbins=%d)", natoms, (long long)nsamples, nbins);
+  for (int k = 1; k < nbins; k++) if (!(edges[k] > edges[k - 1])) return nm_fail_msg(NM_EINVAL, "nm_rdf_counts: edges must increase strictly");
+  if (nsamples == 0) return NM_OK;
+  int ndev = nm_device_count();
+  if (ndev < 0) return ndev;
+  if (device < 0 || device >= ndev) return nm_fail_msg(NM_ENODEV, "nm_rdf_counts: device %d not in [0,%d)", device, ndev);
+  int rc = NM_OK;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  float *d_pos = nullptr, *d_box = nullptr, *d_thr = nullptr; uint32_t* d_cnt = nullptr;
+  std::vector<float> thr(nbins);
+  // float32 thresholds exactly equivalent to the float64 edge tests of np.histogram
+  for (int k = 0; k < nbins; k++) {
+    float f = (float)edges[k];
+    if ((double)f < edges[k]) f = nextafterf(f, INFINITY);
+    thr[k] = f;
+  }
+  float t_top = (float)edges[nbins - 1];
+  if ((double)t_top > edges[nbins - 1]) t_top = nextafterf(t_top, -INFINITY);
+  RdfParams p;
+  p.N = natoms; p.nb = nbins; p.t_top = t_top;
+  p.cut = t_top * (1.0f + 4e-6f) + 1e-30f;
+  p.inv_dr = (float)((nbins - 1) / (edges[nbins - 1] - edges[0]));
+  {
+    RCK(cudaSetDevice(device));
+    const size_t nposb = sizeof(float) * 3 * (size_t)natoms * nsamples, ncntb = sizeof(uint32_t) * (size_t)nbins * nsamples;
+    RCK(cudaMalloc(&d_thr, sizeof(float) * nbins));
+    RCK(cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * nbins, cudaMemcpyHostToDevice, st));
+    if (dev_ptrs) { d_pos = const_cast<float*>(pos); d_box = const_cast<float*>(box); d_cnt = counts; }
+    else {
+      RCK(cudaMalloc(&d_pos, nposb)); RCK(cudaMalloc(&d_box, sizeof(float) * nsamples)); RCK(cudaMalloc(&d_cnt, ncntb));
+      RCK(cudaMemcpyAsync(d_pos, pos, nposb, cudaMemcpyHostToDevice, st));
+      RCK(cudaMemcpyAsync(d_box, box, sizeof(float) * nsamples, cudaMemcpyHostToDevice, st));
+    }
+    RCK(cudaMemsetAsync(d_cnt, 0, ncntb, st));
+    // split the 'a' range of a sample over several CTAs when there are too few samples to fill the GPU
+    int nsplit = 1;
+    if (nsamples < 2 * 148) nsplit = (int)((2 * 148 + nsamples - 1) / nsamples);
+    int a_chunk = (natoms + nsplit - 1) / nsplit;
+    if (a_chunk < 64) a_chunk = natoms < 64 ? natoms : 64;
+    if (a_chunk > 2048) a_chunk = 2048;      // 24 KB of positions + the private histogram: two CTAs per SM
+    nsplit = (natoms + a_chunk - 1) / a_chunk;
+    p.a_chunk = a_chunk;
+    const size_t base = sizeof(float) * (3 * (size_t)a_chunk + nbins);
+    p.private_hist = (base + sizeof(uint32_t) * (size_t)nbins * T) <= 200 * 1024;
+    const size_t smem = base + sizeof(uint32_t) * (size_t)nbins * (p.private_hist ? T : 1);
+    RCK(cudaFuncSetAttribute(k_rdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.pos = d_pos; p.box = d_box; p.counts = d_cnt; p.thr = d_thr;
+    for (int64_t s0 = 0; s0 < nsamples; s0 += 65535) {       // gridDim.y limit
+      const int ns = (int)((nsamples - s0) < 65535 ? (nsamples - s0) : 65535);
+      RdfParams q = p;
+      q.pos = d_pos + 3 * (size_t)natoms * s0; q.box = d_box + s0; q.counts = d_cnt + (size_t)nbins * s0;
+      k_rdf<<<dim3(nsplit, ns), T, smem, st>>>(q);
+      RCK(cudaGetLastError());
+    }
+    if (!dev_ptrs) {
+      RCK(cudaMemcpyAsync(counts, d_cnt, ncntb, cudaMemcpyDeviceToHost, st));
+      RCK(cudaStreamSynchronize(st));
+    }
+  }
+done:
+  if (rc != NM_OK) cudaStreamSynchronize(st);
+  else if (!dev_ptrs) { /* already synchronised */ }
+  if (d_thr) { cudaStreamSynchronize(st); cudaFree(d_thr); }
+  if (!dev_ptrs) { if (d_pos) cudaFree(d_pos); if (d_box) cudaFree(d_box); if (d_cnt) cudaFree(d_cnt); }
+  (void)g_rdf_err;
+  return rc;
+}

@@ -1,0 +1,249 @@
+"""GPU parity tests: the CUDA path through the C-ABI against the CPU oracle (same seeded inputs)
+and against the golden fixtures made from the reference's own functions."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+A0 = (4 / 1.122) ** (1 / 3)      # fcc constant at the reference's lattice density (lammps_remcmc.py:340,883)
+
+
+def _configs(orc, n_side, rho_list, sigma_list, seed):
+    rng = np.random.default_rng(seed)
+    xs, boxes = [], []
+    for rho, sig in zip(rho_list, sigma_list):
+        box = n_side * (4 / rho) ** (1 / 3)
+        x = orc.fcc_positions(n_side, box) + rng.normal(0, sig, (4 * n_side ** 3, 3))
+        xs.append(orc.wrap(x.reshape(-1), box))
+        boxes.append(box)
+    return np.array(xs), np.array(boxes)
+
+
+# ------------------------------------------------------------------ a-1 energy / virial / forces
+@pytest.mark.parametrize("n_side", [4, 5, 7, 10])
+def test_lj_eval_matches_oracle(nm, orc, n_side):
+    """tolerance (north star): 1e-10 relative in FP64 for energy, virial and forces"""
+    rho = [1.122, 1.17, 1.0, 0.8, 0.55, 0.42]
+    sig = [0.0, 0.05, 0.12, 0.25, 0.35, 0.5]
+    x, box = _configs(orc, n_side, rho, sig, seed=n_side)
+    n = 4 * n_side ** 3
+    with nm.Engine(natoms=n, n_rep=len(box), nt=len(box)) as eng:
+        eng.set_state(x=x, box=box)
+        pe, w, f, npairs = eng.eval()
+        st = eng.get_state()
+    for k in range(len(box)):
+        pe_o, w_o, f_o, np_o = orc.lj_eval_list(x[k], box[k])
+        assert npairs[k] == np_o
+        assert abs(pe[k] - pe_o) <= 1e-10 * abs(pe_o)
+        assert abs(w[k] - w_o) <= 1e-10 * max(abs(w_o), abs(pe_o))
+        fscale = max(np.abs(f_o).max(), 1.0)
+        assert np.abs(f[k] - f_o).max() <= 1e-10 * fscale
+        assert np.abs(f[k].sum(0)).max() <= 1e-9 * fscale          # Newton's third law
+        np.testing.assert_allclose(st["x"][k], x[k], rtol=0, atol=1e-15)
+
+
+def test_lj_eval_fcc_anchor(nm, orc):
+    """perfect fcc at rho*=1.122: E/N and W/(3V) against the analytic shell sums"""
+    e_shell, w_shell, nn = orc.fcc_shell_sum(A0)
+    for sz in (4, 5):
+        n, box = 4 * sz ** 3, sz * A0
+        x = orc.fcc_positions(sz, box).reshape(1, -1)
+        with nm.Engine(natoms=n, n_rep=1, nt=1) as eng:
+            eng.set_state(x=x, box=[box])
+            pe, w, f, npairs = eng.eval()
+        assert npairs[0] == n * nn // 2
+        assert abs(pe[0] / n - e_shell) < 1e-12 * abs(e_shell)
+        assert abs(w[0] / n - w_shell) < 1e-12 * abs(w_shell)
+        assert np.abs(f).max() < 1e-11
+
+
+def test_box_too_small_is_an_error(nm, orc):
+    x = orc.fcc_positions(3, 4.9).reshape(1, -1)
+    with nm.Engine(natoms=108, n_rep=1, nt=1) as eng:
+        with pytest.raises(nm.NmError) as ei:
+            eng.set_state(x=x, box=[4.9])
+        assert ei.value.code == nm.NM_EBOX
+
+
+# ------------------------------------------------------------------ a-2..a-9 cycle, move by move
+def _run_both(nm, orc, n_side, bulk, mod, ncycles, rho, temps, press, seed=256, dx0=0.03125):
+    n = 4 * n_side ** 3
+    nrep = len(temps)
+    x, box = _configs(orc, n_side, rho, [0.05] * nrep, seed=11)
+    box = np.array([orc.round6(b) for b in box])
+    T = np.array(temps, dtype=np.float32).astype(np.float64)
+    P = np.array(press, dtype=np.float32).astype(np.float64)
+    labels = np.stack([T, P / T, T, [orc.round6(t) for t in T]], 1)
+    params = orc.make_params(mod=mod, bulk_move=int(bulk), seed=seed)
+    xo, vo = x.copy(), np.zeros_like(x)
+    scal = np.stack([box, np.full(nrep, dx0), np.full(nrep, 0.03125), np.full(nrep, 0.00390625)], 1).copy()
+    counts = np.zeros((nrep, 6))
+    th_o = []
+    for cyc in range(ncycles):
+        rows = []
+        for k in range(nrep):
+            th, _ = orc.cycle(params, labels[k], k, cyc, xo[k], vo[k], scal[k], counts[k])
+            rows.append(th)
+            scal[k, 1:] = orc.adapt(scal[k, 1:], th[15:18])
+            counts[k] = 0
+        th_o.append(np.array(rows))
+    th_g = []
+    with nm.Engine(natoms=n, n_rep=nrep, nt=nrep, mod=mod, bulk_move=bulk, seed=seed) as eng:
+        eng.set_labels(labels[:, 0], labels[:, 1], labels[:, 2], labels[:, 3])
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(nrep, dx0), dv=np.full(nrep, 0.03125),
+                      dt=np.full(nrep, 0.00390625))
+        for cyc in range(ncycles):
+            eng.run_cycle(cyc)
+            th_g.append(eng.get_thermo())
+            eng.adapt()
+        st = eng.get_state()
+        ct = eng.counters()
+    return np.array(th_o), np.array(th_g), (xo, vo, scal), st, ct
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+def test_cycle_matches_oracle_move_by_move(nm, orc, bulk):
+    """same counter-based RNG on both sides: identical accept decisions, energies to 1e-9"""
+    th_o, th_g, (xo, vo, scal), st, ct = _run_both(nm, orc, 4, bulk, mod=24, ncycles=3,
+                                                   rho=[1.1, 1.0, 0.85, 0.6], temps=[0.4, 0.9, 1.6, 2.5],
+                                                   press=[1, 3, 5, 8])
+    # counters and acceptance ratios are integers / float32 ratios: exact
+    np.testing.assert_array_equal(th_g[..., 9:15], th_o[..., 9:15])
+    np.testing.assert_array_equal(th_g[..., 15:18], th_o[..., 15:18])
+    np.testing.assert_allclose(th_g[..., :9], th_o[..., :9], rtol=2e-9, atol=1e-9)
+    np.testing.assert_allclose(st["box"], scal[:, 0], rtol=0, atol=0)
+    np.testing.assert_allclose(st["dx"], scal[:, 1], rtol=1e-15)
+    np.testing.assert_allclose(st["dt"], scal[:, 3], rtol=1e-15)
+    d = st["x"] - xo
+    d -= st["box"][:, None] * np.rint(d / st["box"][:, None])
+    assert np.abs(d).max() < 1e-8
+    assert np.abs(st["v"] - vo).max() < 1e-8
+    assert ct["sweeps"] == 4 * 24 * 3
+    assert ct["hmc_atom_steps"] == 256 * 8 * ct["hmc_moves"]
+
+
+def test_cycle_hmc_only_energy_conservation(nm, orc):
+    """pure HMC (ppos = pvol = 0) at tiny dt must accept ~everything; |dH| scales as dt^2"""
+    n_side, n = 4, 256
+    x, box = _configs(orc, n_side, [1.0], [0.05], seed=3)
+    for dt, lim in ((0.001, 0.02), (0.004, 0.3)):
+        with nm.Engine(natoms=n, n_rep=1, nt=1, mod=32, ppos=0.0, pvol=0.0, text_rounding=False) as eng:
+            eng.set_labels([1.0], [1.0], [1.0], [1.0])
+            eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[0.03], dv=[0.03], dt=[dt])
+            eng.run_cycle(0)
+            th = eng.get_thermo()[0]
+        assert th[13] == 32
+        assert th[14] >= 32 * (1 - lim)
+        assert abs(th[0] - 1.0) < 0.2        # kinetic temperature near the target
+
+
+# ------------------------------------------------------------------ a-10 adaptation
+def test_adapt_matches_reference_golden(nm, orc):
+    gold = json.load(open(os.path.join(GOLDEN, "host_reference.json")))["adapt"]
+    # drive the ratios through a real cycle is not possible; instead check the kernel through a one-move cycle:
+    # with mod=0 the ratios are 0/0 -> 0 -> every step shrinks (the reference's "no tries" behaviour)
+    x, box = _configs(orc, 4, [1.0], [0.02], seed=5)
+    with nm.Engine(natoms=256, n_rep=1, nt=1, mod=0) as eng:
+        eng.set_labels([1.0], [1.0], [1.0], [1.0])
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[0.03125], dv=[0.0625], dt=[0.00390625])
+        eng.run_cycle(0)
+        th = eng.get_thermo()[0]
+        assert th[15] == 0 and th[16] == 0 and th[17] == 0
+        eng.adapt()
+        st = eng.get_state(want_x=False, want_v=False)
+    c = [g for g in gold if g["nap"] == 0 and g["ntp"] == 0][0]
+    assert st["dx"][0] == c["dx"] and st["dv"][0] == c["dv"] and st["dt"][0] == c["dt"]
+
+
+# ------------------------------------------------------------------ a-11 replica exchange
+@pytest.mark.parametrize("name", ["g2x4", "g4x8", "g3x6_anti", "g2x5_inf"])
+def test_exchange_matches_reference_golden(nm, orc, name):
+    """bit-exact swap decisions given the reference's energies and np.random uniforms"""
+    g = np.load(os.path.join(GOLDEN, "exchange_reference.npz"))
+    np_, nt = (int(v) for v in g[name + "_shape"])
+    ns = np_ * nt
+    n = 256
+    # build configurations whose (pe + ke, vol) the engine will report: we cannot dictate pe, so inject the
+    # golden table directly through the pack/apply split (the all-gather payload) instead
+    import torch
+    table = torch.tensor(np.stack([g[name + "_pe"] + g[name + "_ke"], g[name + "_vol"]], 1), device="cuda")
+    x, box = _configs(orc, 4, [1.0] * ns, [0.02] * ns, seed=9)
+    with nm.Engine(natoms=n, n_rep=ns, nt=nt, mod=0) as eng:
+        eng.set_labels(g[name + "_et"], g[name + "_pf"], g[name + "_et"], g[name + "_et"])
+        dx0 = g[name + "_dx"]
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=dx0, dv=dx0, dt=dx0)
+        perm, swaps = eng.exchange_apply(table.data_ptr(), g[name + "_et"], g[name + "_pf"], 0,
+                                         uniforms=g[name + "_uniforms"])
+        st = eng.get_state()
+    np.testing.assert_array_equal(perm, g[name + "_perm"])
+    perm_o, swaps_o = orc.exchange(np_, nt, g[name + "_pe"] + g[name + "_ke"], g[name + "_vol"], g[name + "_et"],
+                                   g[name + "_pf"], g[name + "_uniforms"])
+    assert swaps == swaps_o
+    # STATE[:12] moved with the swap: configuration and its step sizes now sit in the new slot
+    np.testing.assert_array_equal(st["dx"], dx0[perm])
+    np.testing.assert_array_equal(st["x"], x[perm])
+    np.testing.assert_array_equal(st["box"], box[perm])
+
+
+def test_exchange_engine_stream_matches_oracle(nm, orc):
+    """without injected uniforms the engine's counter-based stream is used; the oracle replays it"""
+    np_, nt, n = 2, 6, 256
+    ns = np_ * nt
+    x, box = _configs(orc, 4, list(np.linspace(1.1, 0.7, ns)), [0.05] * ns, seed=21)
+    T = np.tile(np.linspace(0.5, 2.0, nt), np_)
+    P = np.repeat([1.0, 4.0], nt)
+    with nm.Engine(natoms=n, n_rep=ns, nt=nt, mod=8, seed=99) as eng:
+        eng.set_labels(T, P / T, T)
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(ns, .03), dv=np.full(ns, .03), dt=np.full(ns, .004))
+        eng.run_cycle(0)
+        th = eng.get_thermo()
+        eng.adapt()
+        perm, swaps = eng.exchange(5)
+    u = orc.exchange_uniforms(99, 5, np_ * nt * (nt - 1) // 2)
+    perm_o, swaps_o = orc.exchange(np_, nt, th[:, 1] + th[:, 2], th[:, 5], T, P / T, u)
+    np.testing.assert_array_equal(perm, perm_o)
+    assert swaps == swaps_o
+
+
+# ------------------------------------------------------------------ a-14 RDF
+@pytest.mark.parametrize("name", ["n108", "n256", "n500"])
+def test_rdf_matches_reference_golden(nm, orc, name):
+    """bin counts bit-exact against lammps_distr.calculate_rdf run in the build container"""
+    g = np.load(os.path.join(GOLDEN, "rdf_reference.npz"))
+    pos, box, r, ref, nat = (g["%s_%s" % (name, f)] for f in ("pos", "box", "r", "g", "natoms"))
+    counts = nm.rdf_counts(pos, box, r)
+    assert counts.dtype == np.uint32 and counts.shape == ref.shape
+    np.testing.assert_array_equal(counts.astype(np.float32) / nat[:, None].astype(np.float32), ref)
+    for s in range(pos.shape[0]):
+        np.testing.assert_array_equal(counts[s], orc.rdf_counts(pos[s], box[s], r))
+
+
+def test_rdf_ragged_and_edge_cases(nm, orc):
+    rng = np.random.default_rng(1)
+    # tiny systems, a single atom, atoms outside the box, a sample whose box equals the minimum box
+    for n in (1, 2, 33, 257):
+        box = np.array([3.0, 3.5, 4.25], dtype=np.float32)
+        pos = (rng.uniform(-0.2, 1.2, (3, n, 3)) * box[:, None, None]).astype(np.float32)
+        for sb in (2, 5, 64, 200):
+            r = orc.rdf_edges(box, sb)
+            got = nm.rdf_counts(pos, box, r)
+            for s in range(3):
+                np.testing.assert_array_equal(got[s], orc.rdf_counts(pos[s], box[s], r))
+    assert nm.rdf_counts(np.zeros((0, 4, 3), np.float32), np.zeros(0, np.float32), np.linspace(0.1, 1, 8)).shape == (0, 8)
+
+
+def test_rdf_large_sample_property(nm, orc):
+    """N=4000: total count = ordered pairs inside (r0, rmax]; permutation invariance; matches oracle on 1 sample"""
+    rng = np.random.default_rng(2)
+    n, box = 4000, np.float32(16.3)
+    pos = rng.uniform(0, float(box), (2, n, 3)).astype(np.float32)
+    pos[1] = pos[0][rng.permutation(n)]
+    r = orc.rdf_edges(np.array([box, box]), 64)
+    got = nm.rdf_counts(pos, np.array([box, box]), r)
+    np.testing.assert_array_equal(got[0], got[1])
+    np.testing.assert_array_equal(got[0], orc.rdf_counts(pos[0], box, r))

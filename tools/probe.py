@@ -1,0 +1,50 @@
+"""ad-hoc timing probe (development aid, not the benchmark)"""
+import sys, time
+import numpy as np
+sys.path.insert(0, ".")
+from neuralmelting_b200 import engine as nm
+from oracle import oracle as orc
+
+def grid(n_side, np_, nt):
+    n = 4 * n_side ** 3
+    P = np.linspace(1, 8, np_, dtype=np.float32).astype(float)
+    T = np.linspace(0.25, 2.5, nt, dtype=np.float32).astype(float)
+    rng = np.random.default_rng(0)
+    xs, boxes, et, pf, tt = [], [], [], [], []
+    for i in range(np_):
+        for j in range(nt):
+            rho = 1.05 - 0.35 * (T[j] - 0.25) / 2.25 + 0.02 * (P[i] - 1)
+            box = n_side * (4 / rho) ** (1 / 3)
+            x = orc.fcc_positions(n_side, box) + rng.normal(0, 0.03, (n, 3))
+            xs.append(orc.wrap(x.reshape(-1), box)); boxes.append(box); et.append(T[j]); pf.append(P[i] / T[j]); tt.append(T[j])
+    return n, np.array(xs), np.array(boxes), np.array(et), np.array(pf), np.array(tt)
+
+def main():
+    n_side, np_, nt = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    ncyc = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    bulk = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+    skin = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
+    n, x, box, et, pf, tt = grid(n_side, np_, nt)
+    ns = np_ * nt
+    for prec in (64, 32):
+        fl, ms = nm.measure_fma_peak(0, prec)
+        print("fma peak fp%d: %.2f TFLOP/s (%.3f ms)" % (prec, fl / 1e12, ms))
+    eng = nm.Engine(natoms=n, n_rep=ns, nt=nt, bulk_move=bool(bulk), skin=skin)
+    eng.set_labels(et, pf, tt)
+    t0 = time.time()
+    eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(ns, .03125), dv=np.full(ns, .03125), dt=np.full(ns, .00390625))
+    print("set_state %.3f s" % (time.time() - t0))
+    for cyc in range(ncyc):
+        eng.reset_counters()
+        t0 = time.time()
+        eng.run_cycle(cyc); eng.synchronize()
+        dt = time.time() - t0
+        th = eng.get_thermo(); eng.adapt(); perm, sw = eng.exchange(cyc)
+        ct = eng.counters()
+        flops = 24.0 * ct["pairs_force"] + 30.0 * ct["pairs_full"]
+        print("cycle %d: %.1f ms  atom-steps/s %.3e  sweeps/s %.3e  pair-flops %.2f TF/s  builds %d evals %d  listpairs/inpairs %.2f swaps %d  <ah> %.2f <av> %.2f <ap> %.2f" % (
+            cyc, dt * 1e3, ct["hmc_atom_steps"] / dt, ct["sweeps"] / dt, flops / dt / 1e12, ct["list_builds"], ct["force_evals"],
+            ct["list_pairs"] / max(1, ct["pairs_force"] + ct["pairs_full"]), sw, th[:, 17].mean(), th[:, 16].mean(), th[:, 15].mean()))
+    print("T col0 thermo:", np.round(th[:nt, :6], 3)[::max(1, nt // 4)])
+
+main()
