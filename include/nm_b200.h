@@ -55,7 +55,7 @@ enum nm_thermo_col {
 
 /* counters returned by nm_get_counters (uint64 each, summed over local replicas
  * since nm_create or the last nm_reset_counters) */
-#define NM_COUNTER_WIDTH 12
+#define NM_COUNTER_WIDTH 16
 enum nm_counter_col {
   NM_CT_SWEEPS = 0,        /* move_mc calls (lammps_remcmc.py:677-679)            */
   NM_CT_HMC_MOVES,         /* hamiltonian_mc calls                                */
@@ -68,7 +68,11 @@ enum nm_counter_col {
   NM_CT_PAIRS_FULL,        /* in-cutoff unordered pairs, force+energy+virial      */
   NM_CT_PAIRS_DELTA,       /* in-cutoff neighbours visited by single-atom dE      */
   NM_CT_LIST_BUILDS,       /* Verlet-list rebuilds                                */
-  NM_CT_LIST_PAIRS         /* listed (candidate) unordered pairs touched          */
+  NM_CT_LIST_PAIRS,        /* listed (candidate) unordered pairs touched          */
+  NM_CT_CLK_EVAL,          /* SM clocks spent in force evaluations (summed over CTAs) */
+  NM_CT_CLK_BUILD,         /* SM clocks spent in list builds                      */
+  NM_CT_CLK_TOTAL,         /* SM clocks of the cycle kernels                      */
+  NM_CT_RESERVED
 };
 
 typedef struct nm_engine nm_engine;   /* opaque */

@@ -84,6 +84,8 @@ __device__ __forceinline__ double wrap1(double x, double L) {
   if (x < 0.0) x = 0.0;
   return x;
 }
+// general re-wrap of a coordinate that may be any number of boxes away
+__device__ __forceinline__ double wrapg(double x, double L) { return wrap1(x - floor(x / L) * L, L); }
 // exact minimum image for wrapped coordinates (|d| < L)
 __device__ __forceinline__ double mic_exact(double d, double L, double hL) {
   if (d > hL) d -= L; else if (d < -hL) d += L;

@@ -23,18 +23,22 @@ namespace nm {
 constexpr int NCMAX = 8;                 // cell grid is at most 8^3
 constexpr int RED_DOUBLES = 32 * 12 + 12;
 constexpr int BC_DOUBLES = 32;
+constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
 constexpr int ST_BOX = 1, ST_NEIGH = 2;  // status bits
 
 // ------------------------------------------------------------------ device-side engine description
 struct Dev {
-  int N, Npad, nrep, nrep_global, rep_offset, nt, maxq;   // maxq = list capacity in quads
+  int N, Npad, nrep, nrep_global, rep_offset, nt, maxq, maxnb;   // list capacity in quads / scratch entries
   int nstps, mod, bulk, text_rounding;
   double ppos, pvol, lat, mass, rc, skin;
   uint32_t seed_lo, seed_hi;
   // per configuration
   double *x, *v, *f, *xs, *vs, *fs, *x0;   // [nrep][3][Npad]
-  ushort4* list;                           // [nrep][maxq][Npad]
-  uint16_t* nnb;                           // [nrep][Npad]
+  ushort4* list;                           // [nrep][maxq][Npad]  neighbour quads, grouped by periodic image
+  uint8_t* qcode;                          // [nrep][maxq][Npad]  image code (0..26) of each quad
+  uint32_t* ltmp;                          // [nrep][maxnb][Npad] build scratch: j | code << 16 in discovery order
+  uint16_t* nnb;                           // [nrep][Npad]        number of quads of atom i
+  int* micmode;                            // [nrep] 1: box < 2(rc+skin) at build, images resolved per pair
   double *box, *pe, *w, *ke, *L0;          // [nrep]
   double *step;                            // [nrep][3]  dx dv dt
   double *cnt;                             // [nrep][6]  ntp nap ntv nav nth nah
@@ -51,22 +55,27 @@ struct Dev {
 struct Ctx {
   int N, Npad, c;
   double L, L0, thr2;           // box, list build box, squared displacement budget (build-box units)
-  double *sx, *sy, *sz;         // shared positions
+  double Lsave;                 // box the saved copy (gxs) refers to
+  double* sp;                   // shared positions, AoS: atom j at sp[3j..3j+2] (one address register per gather)
+  float4* sf;                   // shared float32 fractional positions (list build prefilter only)
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
   uint16_t *cell_atoms, *atom_cell;
   unsigned long long* s_pairs;  // shared: in-cutoff ordered pairs of force-only evaluations
   // global views of this configuration
   double *gx, *gv, *gf, *gxs, *gvs, *gfs, *gx0;
-  ushort4* list; uint16_t* nnb;
+  ushort4* list; uint8_t* qcode; uint32_t* ltmp; uint16_t* nnb;
+  double* sht;                  // shared: 27 image shift vectors (k*L) for the current box
+  int mic;                      // minimum image per pair (small boxes) instead of stored image codes
   unsigned long long ct[NM_COUNTER_WIDTH];   // meaningful on thread 0 only
   double list_pairs;
   int status;
 };
 
 __host__ __device__ inline size_t smem_bytes(int Npad) {
-  size_t b = sizeof(double) * (3 * (size_t)Npad + RED_DOUBLES + BC_DOUBLES);
-  b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8);
+  size_t b = sizeof(double) * (3 * (size_t)Npad + RED_DOUBLES + BC_DOUBLES + SHT_DOUBLES);
+  b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8 + 2);   // +2: keeps the float4 block 16-byte aligned
+  b += sizeof(float4) * (size_t)Npad;
   b += sizeof(unsigned long long) * 2;
   b += sizeof(uint16_t) * 2 * (size_t)Npad;
   return b;
@@ -75,22 +84,27 @@ __host__ __device__ inline size_t smem_bytes(int Npad) {
 __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned char* smem) {
   cx.N = d.N; cx.Npad = d.Npad; cx.c = c;
   double* p = reinterpret_cast<double*>(smem);
-  cx.sx = p; cx.sy = p + d.Npad; cx.sz = p + 2 * d.Npad; p += 3 * d.Npad;
+  cx.sp = p; p += 3 * d.Npad;
   cx.red = p; p += RED_DOUBLES;
   cx.bc = p; p += BC_DOUBLES;
+  cx.sht = p; p += SHT_DOUBLES;
   cx.s_pairs = reinterpret_cast<unsigned long long*>(p); p += 2;
   int* q = reinterpret_cast<int*>(p);
   cx.cell_cnt = q; q += NCMAX * NCMAX * NCMAX + 1;
   cx.cell_start = q; q += NCMAX * NCMAX * NCMAX + 1;
-  cx.ibc = q; q += 8;
+  cx.ibc = q; q += 8 + 2;
+  cx.sf = reinterpret_cast<float4*>(q); q += 4 * d.Npad;
   uint16_t* h = reinterpret_cast<uint16_t*>(q);
   cx.cell_atoms = h; cx.atom_cell = h + d.Npad;
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
   cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off; cx.gx0 = d.x0 + off;
   cx.list = d.list + (size_t)c * d.maxq * d.Npad;
+  cx.qcode = d.qcode + (size_t)c * d.maxq * d.Npad;
+  cx.ltmp = d.ltmp + (size_t)c * d.maxnb * d.Npad;
   cx.nnb = d.nnb + (size_t)c * d.Npad;
-  cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.list_pairs = d.list_pairs[c];
+  cx.mic = d.micmode[c];
+  cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.Lsave = cx.L; cx.list_pairs = d.list_pairs[c];
   cx.status = 0;
   for (int k = 0; k < NM_COUNTER_WIDTH; k++) cx.ct[k] = 0;
   if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; }
@@ -110,34 +124,54 @@ __device__ __forceinline__ double disp2(const Ctx& cx, int i, double x, double y
   return (ux * ux + uy * uy + uz * uz) * cx.L0 * cx.L0;
 }
 
-// positions global -> shared (wrapped), plus the far-away dummy atom that pads the list
+// positions global -> shared, plus the far-away dummy atom that pads the list. Positions are CONTINUOUS between
+// list builds (an atom may sit slightly outside [0,L)): the list stores the periodic image of every pair, so
+// atoms are re-wrapped only when the list is rebuilt.
 __device__ void load_positions(const Dev& d, Ctx& cx) {
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
-    cx.sx[i] = wrap1(cx.gx[i], cx.L); cx.sy[i] = wrap1(cx.gx[cx.Npad + i], cx.L); cx.sz[i] = wrap1(cx.gx[2 * cx.Npad + i], cx.L);
+    cx.sp[3 * i] = cx.gx[i]; cx.sp[3 * i + 1] = cx.gx[cx.Npad + i]; cx.sp[3 * i + 2] = cx.gx[2 * cx.Npad + i];
   }
-  for (int i = cx.N + threadIdx.x; i < cx.Npad; i += blockDim.x) { cx.sx[i] = 1e9; cx.sy[i] = 1e9; cx.sz[i] = 1e9; }
+  for (int i = cx.N + threadIdx.x; i < cx.Npad; i += blockDim.x) { cx.sp[3 * i] = 1e9; cx.sp[3 * i + 1] = 1e9; cx.sp[3 * i + 2] = 1e9; }
 }
 __device__ void store_positions(Ctx& cx) {
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
-    cx.gx[i] = cx.sx[i]; cx.gx[cx.Npad + i] = cx.sy[i]; cx.gx[2 * cx.Npad + i] = cx.sz[i];
+    cx.gx[i] = cx.sp[3 * (i)]; cx.gx[cx.Npad + i] = cx.sp[3 * (i) + 1]; cx.gx[2 * cx.Npad + i] = cx.sp[3 * (i) + 2];
   }
 }
 
 // ------------------------------------------------------------------ Verlet list build (cell binned, deterministic)
+// Produces, per atom i, neighbour quads GROUPED BY PERIODIC IMAGE: every quad carries one image code
+// (kx+1)*9 + (ky+1)*3 + (kz+1), k = rint((x_i - x_j)/L), so the force loop subtracts the image shift once per
+// quad from x_i and needs no per-pair minimum-image arithmetic. Groups are padded to whole quads with the
+// far-away dummy atom N. Atoms are re-wrapped into [0,L) here (and only here); the saved copy used for move
+// reverts is shifted by the same lattice vector so that a revert stays consistent with the new list.
 __device__ void build_list(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
-  const double L = cx.L, hL = 0.5 * L, rl = d.rc + d.skin, rl2 = rl * rl, invL = 1.0 / L;
-  int nc = (int)floor(L / rl);
+  const double L = cx.L, rl = d.rc + d.skin, rl2 = rl * rl, invL = 1.0 / L;
+  int nc = (int)floor(L / (rl * (1.0 + 1e-4)));
   if (nc > NCMAX) nc = NCMAX;
   if (nc < 3) nc = 1;
   const int ncell = nc * nc * nc;
+  const long long t_build0 = clock64();
+  __syncthreads();
+  // wrap + float32 fractional copies: the neighbour search runs entirely on the FP32 pipe. A pair enters the list
+  // when its float32 distance is below rl*(1+margin); the margin covers the float32 rounding of the fractional
+  // coordinates (<= 2^-24 each, < 4e-6 relative on r^2 at r ~ rl), so the list is a superset of {r < rl}.
+  for (int i = tid; i < N; i += nthr) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const double x = cx.sp[3 * i + a], xw = wrap1(x - floor(x * invL) * L, L);
+      if (xw != x) { cx.sp[3 * i + a] = xw; cx.gxs[a * Npad + i] += (xw - x) * (cx.Lsave * invL); }
+    }
+    cx.sf[i] = make_float4((float)(cx.sp[3 * i] * invL), (float)(cx.sp[3 * i + 1] * invL), (float)(cx.sp[3 * i + 2] * invL), 0.f);
+  }
   __syncthreads();
   if (nc > 1) {
     for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
     __syncthreads();
     for (int i = tid; i < N; i += nthr) {
-      int a = min(nc - 1, (int)(cx.sx[i] * invL * nc)), b = min(nc - 1, (int)(cx.sy[i] * invL * nc)),
-          e = min(nc - 1, (int)(cx.sz[i] * invL * nc));
+      const float4 p = cx.sf[i];
+      int a = min(nc - 1, (int)(p.x * nc)), b = min(nc - 1, (int)(p.y * nc)), e = min(nc - 1, (int)(p.z * nc));
       int c = (a * nc + b) * nc + e;
       cx.atom_cell[i] = (uint16_t)c;
       atomicAdd(&cx.cell_cnt[c], 1);
@@ -172,17 +206,26 @@ __device__ void build_list(const Dev& d, Ctx& cx) {
     }
     __syncthreads();
   }
-  const int maxnb = d.maxq * 4;
   uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
+  const float rl2f = (float)(rl2 * invL * invL * (1.0 + 2e-5));
+  const float magic = 12582912.f;          // 1.5 * 2^23: (x + magic) - magic = rint(x) for |x| < 2^22
   double tot = 0.0; int over = 0;
   for (int i = tid; i < N; i += nthr) {
-    const double xi = cx.sx[i], yi = cx.sy[i], zi = cx.sz[i];
+    const float4 pi = cx.sf[i];
+    unsigned char c27[27];
+#pragma unroll
+    for (int c = 0; c < 27; c++) c27[c] = 0;
     int cnt = 0;
-    auto test = [&](int j) {
-      if (j == i) return;
-      double dx = mic_exact(xi - cx.sx[j], L, hL), dy = mic_exact(yi - cx.sy[j], L, hL), dz = mic_exact(zi - cx.sz[j], L, hL);
-      if (dx * dx + dy * dy + dz * dz < rl2) {
-        if (cnt < maxnb) l16[((size_t)(cnt >> 2) * Npad + i) * 4 + (cnt & 3)] = (uint16_t)j;
+    auto test = [&](int j) {                 // pass A: discovery order -> scratch, count per image code
+      const float4 pj = cx.sf[j];
+      float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      const float kx = __fadd_rn(__fadd_rn(dx, magic), -magic), ky = __fadd_rn(__fadd_rn(dy, magic), -magic),
+                  kz = __fadd_rn(__fadd_rn(dz, magic), -magic);
+      dx -= kx; dy -= ky; dz -= kz;
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      if (r2 < rl2f && j != i) {
+        const int code = (int)kx * 9 + (int)ky * 3 + (int)kz + 13;
+        if (cnt < d.maxnb) { cx.ltmp[(size_t)cnt * Npad + i] = (uint32_t)j | ((uint32_t)code << 16); c27[code]++; }
         cnt++;
       }
     };
@@ -196,23 +239,45 @@ __device__ void build_list(const Dev& d, Ctx& cx) {
         for (int p = s; p < en; p++) test(cx.cell_atoms[p]);
       }
     }
-    if (cnt > maxnb) { over = 1; cnt = maxnb; }
-    for (int k = cnt; k < ((cnt + 3) & ~3); k++) l16[((size_t)(k >> 2) * Npad + i) * 4 + (k & 3)] = (uint16_t)N;
-    cx.nnb[i] = (uint16_t)cnt;
+    if (cnt > d.maxnb) { over = 1; cnt = d.maxnb; }
+    // group offsets (in entries, each group padded to a whole quad)
+    unsigned short cur[27];
+    int nq = 0;
+#pragma unroll
+    for (int c = 0; c < 27; c++) { cur[c] = (unsigned short)(nq * 4); nq += (c27[c] + 3) >> 2; }
+    if (nq > d.maxq) { over = 1; nq = d.maxq; }
+    for (int c = 0, q = 0; c < 27 && q < nq; c++) {
+      const int gq = (c27[c] + 3) >> 2;
+      for (int g = 0; g < gq && q < nq; g++, q++) {
+        cx.qcode[(size_t)q * Npad + i] = (uint8_t)c;
+        cx.list[(size_t)q * Npad + i] = make_ushort4((unsigned short)N, (unsigned short)N, (unsigned short)N, (unsigned short)N);
+      }
+    }
+    for (int t = 0; t < cnt; t++) {          // pass B: counting sort by image code
+      const uint32_t en = cx.ltmp[(size_t)t * Npad + i];
+      const int c = en >> 16, k = cur[c]++;
+      if ((k >> 2) < nq) l16[((size_t)(k >> 2) * Npad + i) * 4 + (k & 3)] = (uint16_t)(en & 0xffffu);
+    }
+    cx.nnb[i] = (uint16_t)nq;
     tot += cnt;
-    cx.gx0[i] = xi * invL; cx.gx0[Npad + i] = yi * invL; cx.gx0[2 * Npad + i] = zi * invL;
+    cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
   }
   double r[2] = { tot, (double)over };
   block_sum<2>(r, cx.red);
   cx.list_pairs = 0.5 * r[0];
   if (r[1] > 0.0) cx.status |= ST_NEIGH;
   cx.L0 = L;
+  cx.mic = L < 2.0 * rl * (1.0 + 1e-3);     // small box: the nearest image of a listed pair may change between builds
   update_thr(d, cx);
-  if (tid == 0) cx.ct[NM_CT_LIST_BUILDS]++;
+  if (tid == 0) { cx.ct[NM_CT_LIST_BUILDS]++; cx.ct[NM_CT_CLK_BUILD] += (unsigned long long)(clock64() - t_build0); }
 }
 
 // barrier after a position update; rebuilds the list if any thread saw its budget exceeded
 __device__ __forceinline__ void sync_and_maybe_build(const Dev& d, Ctx& cx, int flag) {
+  if (threadIdx.x < 27) {                  // image shift vectors k*L of the current box (readers are past a barrier)
+    const int c = threadIdx.x;
+    cx.sht[3 * c] = (c / 9 - 1) * cx.L; cx.sht[3 * c + 1] = ((c / 3) % 3 - 1) * cx.L; cx.sht[3 * c + 2] = (c % 3 - 1) * cx.L;
+  }
   if (__syncthreads_or(flag)) build_list(d, cx);
 }
 // generic pass: is every atom still inside the displacement budget?
@@ -221,7 +286,7 @@ __device__ void check_list(const Dev& d, Ctx& cx) {
   if (!flag) {
     const double invL = 1.0 / cx.L;
     for (int i = threadIdx.x; i < cx.N; i += blockDim.x)
-      flag |= disp2(cx, i, cx.sx[i], cx.sy[i], cx.sz[i], invL) > cx.thr2;
+      flag |= disp2(cx, i, cx.sp[3 * (i)], cx.sp[3 * (i) + 1], cx.sp[3 * (i) + 2], invL) > cx.thr2;
   }
   sync_and_maybe_build(d, cx, flag);
 }
@@ -230,37 +295,68 @@ __device__ void check_list(const Dev& d, Ctx& cx) {
 // EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
 // half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
 // Ends with a barrier: shared positions may be rewritten afterwards.
-template <bool EW, bool KICK>
-__device__ void eval_forces(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
+// one listed pair, image already resolved (xs = x_i - image shift of the quad): rsq, reciprocal by MUFU.RCP64H +
+// one cubic Newton step, LJ force. The cutoff test is a 64-bit INTEGER compare (positive doubles order like
+// integers) and the masking a single select on the high word, so only arithmetic reaches the FP64 pipe:
+// 19 FP64-pipe instructions per pair for forces, +3 for energy and virial.
+// MIC: small boxes -- the minimum image is taken per pair (high-word test + FP64 subtract) instead.
+template <bool EW, bool MIC>
+__device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs, double ys, double zs,
+                                        int L_hi, int L_lo, int hL_hi, long long rc2_bits,
+                                        double& fx, double& fy, double& fz, int& np, double& e, double& vir) {
+  double dx = xs - pj[0], dy = ys - pj[1], dz = zs - pj[2];
+  if (MIC) { dx = mic_fast(dx, L_hi, L_lo, hL_hi); dy = mic_fast(dy, L_hi, L_lo, hL_hi); dz = mic_fast(dz, L_hi, L_lo, hL_hi); }
+  const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
+  const bool in = __double_as_longlong(rsq) < rc2_bits;
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
+  double t = fma(-rsq, y, 1.0);                         // seed is good to ~2^-9: cubic step, then a quadratic one
+  t = fma(t, t, t);
+  y = fma(y, t, y);
+  t = fma(-rsq, y, 1.0);
+  const double r2inv = fma(y, t, y);                    // relative error ~ seed^6 (< 1 ulp)
+  const double r6inv = r2inv * r2inv * r2inv;
+  double fpair = r6inv * fma(48.0, r6inv, -24.0) * r2inv;
+  // outside the cutoff the high word is zeroed: the operand becomes a denormal (< 1e-308) whose products vanish
+  fpair = __hiloint2double(in ? __double2hiint(fpair) : 0, __double2loint(fpair));
+  fx = fma(dx, fpair, fx); fy = fma(dy, fpair, fy); fz = fma(dz, fpair, fz);
+  np += in;
+  if (EW) {
+    double ep = r6inv * fma(4.0, r6inv, -4.0);
+    ep = __hiloint2double(in ? __double2hiint(ep) : 0, __double2loint(ep));
+    e += ep;
+    vir = fma(rsq, fpair, vir);
+  }
+}
+
+// EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
+// half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
+// Ends with a barrier: shared positions may be rewritten afterwards.
+template <bool EW, bool KICK, bool MIC>
+__device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
   const int N = cx.N, Npad = cx.Npad;
-  const double rc2 = d.rc * d.rc;
+  const long long rc2_bits = __double_as_longlong(d.rc * d.rc);
   const int L_hi = __double2hiint(cx.L), L_lo = __double2loint(cx.L), hL_hi = __double2hiint(0.5 * cx.L);
   double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
+  const long long t_eval0 = clock64();
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const double xi = cx.sx[i], yi = cx.sy[i], zi = cx.sz[i];
+    const double xi = cx.sp[3 * i], yi = cx.sp[3 * i + 1], zi = cx.sp[3 * i + 2];
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    const int nq = (cx.nnb[i] + 3) >> 2;
+    const int nq = cx.nnb[i];
     const ushort4* lp = cx.list + i;
+    const uint8_t* cp = cx.qcode + i;
     ushort4 cur = nq > 0 ? lp[0] : make_ushort4(0, 0, 0, 0);
+    int code = (!MIC && nq > 0) ? cp[0] : 13;
     for (int q = 0; q < nq; q++) {
       const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
-      const int jj[4] = { cur.x, cur.y, cur.z, cur.w };
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const int j = jj[t];
-        const double dx = mic_fast(xi - cx.sx[j], L_hi, L_lo, hL_hi);
-        const double dy = mic_fast(yi - cx.sy[j], L_hi, L_lo, hL_hi);
-        const double dz = mic_fast(zi - cx.sz[j], L_hi, L_lo, hL_hi);
-        const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-        const bool in = rsq < rc2;
-        const double r2inv = rcp_nr(rsq);
-        const double r6inv = r2inv * r2inv * r2inv;
-        const double fpair = in ? r6inv * (48.0 * r6inv - 24.0) * r2inv : 0.0;
-        fx = fma(dx, fpair, fx); fy = fma(dy, fpair, fy); fz = fma(dz, fpair, fz);
-        np += in;
-        if (EW) { e += in ? r6inv * (4.0 * r6inv - 4.0) : 0.0; vir = fma(rsq, fpair, vir); }
-      }
-      cur = nxt;
+      const int ncode = (!MIC && q + 1 < nq) ? cp[(size_t)(q + 1) * Npad] : 13;
+      double xs = xi, ys = yi, zs = zi;
+      if (!MIC) { xs -= cx.sht[3 * code]; ys -= cx.sht[3 * code + 1]; zs -= cx.sht[3 * code + 2]; }
+      lj_pair<EW, MIC>(cx.sp + 3 * cur.x, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * cur.y, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * cur.z, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * cur.w, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      cur = nxt; code = ncode;
     }
     cx.gf[i] = fx; cx.gf[Npad + i] = fy; cx.gf[2 * Npad + i] = fz;
     if (KICK) {
@@ -276,13 +372,20 @@ __device__ void eval_forces(const Dev& d, Ctx& cx, double dtf, double (&out)[4])
     if (threadIdx.x == 0) {
       cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_PAIRS_FULL] += (unsigned long long)out[2];
       cx.ct[NM_CT_LIST_PAIRS] += (unsigned long long)cx.list_pairs;
+      cx.ct[NM_CT_CLK_EVAL] += (unsigned long long)(clock64() - t_eval0);
     }
   } else {
     np = __reduce_add_sync(0xffffffffu, np);
     if ((threadIdx.x & 31) == 0) atomicAdd(cx.s_pairs, (unsigned long long)np);
-    if (threadIdx.x == 0) { cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_LIST_PAIRS] += (unsigned long long)cx.list_pairs; }
     __syncthreads();
+    if (threadIdx.x == 0) { cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_LIST_PAIRS] += (unsigned long long)cx.list_pairs;
+                            cx.ct[NM_CT_CLK_EVAL] += (unsigned long long)(clock64() - t_eval0); }
   }
+}
+template <bool EW, bool KICK>
+__device__ __forceinline__ void eval_forces(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
+  if (cx.mic) eval_forces_t<EW, KICK, true>(d, cx, dtf, out);
+  else eval_forces_t<EW, KICK, false>(d, cx, dtf, out);
 }
 
 // the acceptance rule shared by all moves (lammps_remcmc.py:487-500, 532-547, 578-593, 623-638)
@@ -303,11 +406,12 @@ __device__ __forceinline__ bool broadcast_flag(Ctx& cx, bool v) {
 struct Energy { double pe, w; };
 
 __device__ void save_xf(Ctx& cx, bool with_v) {
+  cx.Lsave = cx.L;
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       const int o = a * cx.Npad + i;
-      cx.gxs[o] = (a == 0 ? cx.sx : a == 1 ? cx.sy : cx.sz)[i];
+      cx.gxs[o] = cx.sp[3 * i + a];
       cx.gfs[o] = cx.gf[o];
       if (with_v) cx.gvs[o] = cx.gv[o];
     }
@@ -318,7 +422,7 @@ __device__ void restore_xf(Ctx& cx, bool with_v) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       const int o = a * cx.Npad + i;
-      (a == 0 ? cx.sx : a == 1 ? cx.sy : cx.sz)[i] = cx.gxs[o];
+      cx.sp[3 * i + a] = cx.gxs[o];
       cx.gf[o] = cx.gfs[o];
       if (with_v) cx.gv[o] = cx.gvs[o];
     }
@@ -334,9 +438,9 @@ __device__ void bulk_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
   int flag = cx.thr2 < 0.0;
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
     double u[3]; rng_uniform3(r, (uint32_t)i, P_BULK_DISP, u);
-    const double x = wrap1(cx.sx[i] + dmax * 2.0 * (u[0] - 0.5), cx.L), y = wrap1(cx.sy[i] + dmax * 2.0 * (u[1] - 0.5), cx.L),
-                 z = wrap1(cx.sz[i] + dmax * 2.0 * (u[2] - 0.5), cx.L);
-    cx.sx[i] = x; cx.sy[i] = y; cx.sz[i] = z;
+    const double x = cx.sp[3 * i] + dmax * 2.0 * (u[0] - 0.5), y = cx.sp[3 * i + 1] + dmax * 2.0 * (u[1] - 0.5),
+                 z = cx.sp[3 * i + 2] + dmax * 2.0 * (u[2] - 0.5);
+    cx.sp[3 * (i)] = x; cx.sp[3 * (i) + 1] = y; cx.sp[3 * (i) + 2] = z;
     if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
   }
   sync_and_maybe_build(d, cx, flag);
@@ -370,11 +474,14 @@ __device__ void volume_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double
   double o[4] = { 0, 0, 0, 0 };
   if (box_ok) {
     cx.L = Lnew; update_thr(d, cx);
-    const double invL = 1.0 / Lnew;
+    const double invL = 1.0 / Lnew, invLold = 1.0 / box, dround = scale * box - Lnew;
     int flag = cx.thr2 < 0.0;
     for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
-      const double x = wrap1(scale * cx.sx[i], Lnew), y = wrap1(scale * cx.sy[i], Lnew), z = wrap1(scale * cx.sz[i], Lnew);
-      cx.sx[i] = x; cx.sy[i] = y; cx.sz[i] = z;
+      // the reference scales WRAPPED coordinates by boxnew/box and then periodises with the '%f'-rounded box:
+      // an atom represented k boxes away from [0,L) must land on the same lattice image, hence the k*(boxnew-Lnew)
+      const double kx = floor(cx.sp[3 * i] * invLold), ky = floor(cx.sp[3 * i + 1] * invLold), kz = floor(cx.sp[3 * i + 2] * invLold);
+      const double x = scale * cx.sp[3 * i] - kx * dround, y = scale * cx.sp[3 * i + 1] - ky * dround, z = scale * cx.sp[3 * i + 2] - kz * dround;
+      cx.sp[3 * (i)] = x; cx.sp[3 * (i) + 1] = y; cx.sp[3 * (i) + 2] = z;
       if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
     }
     sync_and_maybe_build(d, cx, flag);
@@ -429,13 +536,13 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
   double xc[3] = { 0, 0, 0 };
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     cx.gv[i] -= vcm[0]; cx.gv[Npad + i] -= vcm[1]; cx.gv[2 * Npad + i] -= vcm[2];
-    xc[0] += m * cx.sx[i]; xc[1] += m * cx.sy[i]; xc[2] += m * cx.sz[i];
+    xc[0] += m * wrapg(cx.sp[3 * i], cx.L); xc[1] += m * wrapg(cx.sp[3 * i + 1], cx.L); xc[2] += m * wrapg(cx.sp[3 * i + 2], cx.L);
   }
   block_sum<3>(xc, cx.red);                                                  // 'velocity all zero angular'
   xc[0] /= (m * N); xc[1] /= (m * N); xc[2] /= (m * N);
   double a[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // L(3), Ixx Iyy Izz Ixy Iyz Ixz
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const double dx = cx.sx[i] - xc[0], dy = cx.sy[i] - xc[1], dz = cx.sz[i] - xc[2];
+    const double dx = wrapg(cx.sp[3 * i], cx.L) - xc[0], dy = wrapg(cx.sp[3 * i + 1], cx.L) - xc[1], dz = wrapg(cx.sp[3 * i + 2], cx.L) - xc[2];
     const double vx = cx.gv[i], vy = cx.gv[Npad + i], vz = cx.gv[2 * Npad + i];
     a[0] += m * (dy * vz - dz * vy); a[1] += m * (dz * vx - dx * vz); a[2] += m * (dx * vy - dy * vx);
     a[3] += m * (dy * dy + dz * dz); a[4] += m * (dx * dx + dz * dz); a[5] += m * (dx * dx + dy * dy);
@@ -454,7 +561,7 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
   }
   t[0] = 0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const double dx = cx.sx[i] - xc[0], dy = cx.sy[i] - xc[1], dz = cx.sz[i] - xc[2];
+    const double dx = wrapg(cx.sp[3 * i], cx.L) - xc[0], dy = wrapg(cx.sp[3 * i + 1], cx.L) - xc[1], dz = wrapg(cx.sp[3 * i + 2], cx.L) - xc[2];
     const double vx = cx.gv[i] - (w1 * dz - w2 * dy), vy = cx.gv[Npad + i] - (w2 * dx - w0 * dz), vz = cx.gv[2 * Npad + i] - (w0 * dy - w1 * dx);
     cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
     t[0] += vx * vx + vy * vy + vz * vz;
@@ -479,8 +586,8 @@ __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, d
       const double vx = fma(dtf, cx.gf[i], cx.gv[i]), vy = fma(dtf, cx.gf[Npad + i], cx.gv[Npad + i]),
                    vz = fma(dtf, cx.gf[2 * Npad + i], cx.gv[2 * Npad + i]);
       cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
-      const double x = wrap1(fma(dt, vx, cx.sx[i]), cx.L), y = wrap1(fma(dt, vy, cx.sy[i]), cx.L), z = wrap1(fma(dt, vz, cx.sz[i]), cx.L);
-      cx.sx[i] = x; cx.sy[i] = y; cx.sz[i] = z;
+      const double x = fma(dt, vx, cx.sp[3 * i]), y = fma(dt, vy, cx.sp[3 * i + 1]), z = fma(dt, vz, cx.sp[3 * i + 2]);
+      cx.sp[3 * (i)] = x; cx.sp[3 * (i) + 1] = y; cx.sp[3 * (i) + 2] = z;
       if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
     }
     sync_and_maybe_build(d, cx, flag);
@@ -509,7 +616,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
   double um[1] = { 0.0 };
   {
     double mx = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmax(mx, disp2(cx, i, cx.sx[i], cx.sy[i], cx.sz[i], invL));
+    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmax(mx, disp2(cx, i, cx.sp[3 * (i)], cx.sp[3 * (i) + 1], cx.sp[3 * (i) + 2], invL));
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     __syncthreads();
     if (lane == 0) cx.red[threadIdx.x >> 5] = mx;
@@ -527,10 +634,8 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
       int kk = k, need = 0;
       for (; kk < N; kk++) {
         double u[3]; rng_uniform3(r, (uint32_t)kk, P_ITER_DISP, u);
-        const double xo = cx.sx[kk], yo = cx.sy[kk], zo = cx.sz[kk];
+        const double xo = cx.sp[3 * (kk)], yo = cx.sp[3 * (kk) + 1], zo = cx.sp[3 * (kk) + 2];
         double xn = xo + 2 * (u[0] - 0.5) * dxs * d.lat, yn = yo + 2 * (u[1] - 0.5) * dxs * d.lat, zn = zo + 2 * (u[2] - 0.5) * dxs * d.lat;
-        xn -= floor(xn / L) * L; yn -= floor(yn / L) * L; zn -= floor(zn / L) * L;
-        xn = wrap1(xn, L); yn = wrap1(yn, L); zn = wrap1(zn, L);
         const double un = sqrt(disp2(cx, kk, xn, yn, zn, invL));
         // every atom within rc of the old or the new position must be in column kk of the list
         const bool list_ok = s * (rl - un - umax) >= rc * (1 + 1e-9) && s * (rl - 2.0 * umax) >= rc * (1 + 1e-9);
@@ -543,8 +648,8 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
         }
         double de = 0.0; int vis = 0;
         auto pair = [&](int j) {
-          const double ax = mic_exact(xn - cx.sx[j], L, hL), ay = mic_exact(yn - cx.sy[j], L, hL), az = mic_exact(zn - cx.sz[j], L, hL);
-          const double bx = mic_exact(xo - cx.sx[j], L, hL), by = mic_exact(yo - cx.sy[j], L, hL), bz = mic_exact(zo - cx.sz[j], L, hL);
+          const double ax = mic_exact(xn - cx.sp[3 * (j)], L, hL), ay = mic_exact(yn - cx.sp[3 * (j) + 1], L, hL), az = mic_exact(zn - cx.sp[3 * (j) + 2], L, hL);
+          const double bx = mic_exact(xo - cx.sp[3 * (j)], L, hL), by = mic_exact(yo - cx.sp[3 * (j) + 1], L, hL), bz = mic_exact(zo - cx.sp[3 * (j) + 2], L, hL);
           const double rn = ax * ax + ay * ay + az * az, ro = bx * bx + by * by + bz * bz;
           if (rn < rc2) { const double r2 = 1.0 / rn, r6 = r2 * r2 * r2; de += r6 * (4.0 * r6 - 4.0); vis++; }
           if (ro < rc2) { const double r2 = 1.0 / ro, r6 = r2 * r2 * r2; de -= r6 * (4.0 * r6 - 4.0); vis++; }
@@ -552,7 +657,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
         if (brute) {
           for (int j = lane; j < N; j += 32) if (j != kk) pair(j);
         } else {
-          const int nq = (cx.nnb[kk] + 3) >> 2;
+          const int nq = cx.nnb[kk];
           for (int q = lane; q < nq; q += 32) {
             const ushort4 e4 = cx.list[(size_t)q * Npad + kk];
             pair(e4.x); pair(e4.y); pair(e4.z); pair(e4.w);
@@ -564,7 +669,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
         if (acc) {
           nacc++; en.pe += de;
           __syncwarp();
-          if (lane == 0) { cx.sx[kk] = xn; cx.sy[kk] = yn; cx.sz[kk] = zn; }
+          if (lane == 0) { cx.sp[3 * (kk)] = xn; cx.sp[3 * (kk) + 1] = yn; cx.sp[3 * (kk) + 2] = zn; }
           __syncwarp();
           umax = fmax(umax, un);
         }
@@ -591,7 +696,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
 // ------------------------------------------------------------------ kernels
 // 'run 0' on the resident configurations: wrap, (re)build list, evaluate; optionally export.
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR, 1)
+__global__ void __launch_bounds__(NTHR, 1024 / NTHR)
 k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npairs_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   Ctx cx; ctx_init(d, cx, blockIdx.x, smem);
@@ -616,7 +721,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
     }
   }
   if (threadIdx.x == 0) {
-    d.pe[cx.c] = o[0]; d.w[cx.c] = o[1]; d.ke[cx.c] = 0.5 * d.mass * t[0]; d.L0[cx.c] = cx.L0; d.list_pairs[cx.c] = cx.list_pairs;
+    d.pe[cx.c] = o[0]; d.w[cx.c] = o[1]; d.ke[cx.c] = 0.5 * d.mass * t[0]; d.L0[cx.c] = cx.L0; d.micmode[cx.c] = cx.mic; d.list_pairs[cx.c] = cx.list_pairs;
     if (pe_out) pe_out[slot] = o[0];
     if (w_out) w_out[slot] = o[1];
     if (npairs_out) npairs_out[slot] = (long long)o[2];
@@ -627,11 +732,12 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
 
 // gen_sample (lammps_remcmc.py:665-691): MOD x move_mc (:643-658), then lammps_extract (:377-391)
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR, 1)
+__global__ void __launch_bounds__(NTHR, 1024 / NTHR)
 k_cycle(Dev d, long long cycle) {
   extern __shared__ __align__(16) unsigned char smem[];
   Ctx cx; ctx_init(d, cx, blockIdx.x, smem);
   const int c = cx.c, slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
+  const long long t_cycle0 = clock64();
   const double et = d.label[4 * slot], pf = d.label[4 * slot + 1], t_vel = d.label[4 * slot + 3];
   const double dxs = d.step[3 * c], dvs = d.step[3 * c + 1], dts = d.step[3 * c + 2];
   load_positions(d, cx);
@@ -669,9 +775,10 @@ k_cycle(Dev d, long long cycle) {
       const float a = (float)cnt[2 * k + 1] / (float)cnt[2 * k];        // float32 ratio, nan_to_num (0/0 -> 0)
       th[NM_TH_AP + k] = isnan(a) ? 0.0 : (double)a;
     }
-    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.list_pairs[c] = cx.list_pairs;
+    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs;
     if (cx.status) d.status[c] |= cx.status;
     cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
+    cx.ct[NM_CT_CLK_TOTAL] += (unsigned long long)(clock64() - t_cycle0);
     for (int k = 0; k < NM_COUNTER_WIDTH; k++) if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]);
   }
 }
@@ -751,7 +858,7 @@ __global__ void k_scatter_state(Dev d, const double* x_aos, const double* v_aos,
   const size_t off = (size_t)c * 3 * Npad;
   for (int i = threadIdx.x; i < N; i += blockDim.x)
     for (int a = 0; a < 3; a++) {
-      if (x_aos) d.x[off + a * Npad + i] = x_aos[((size_t)k * N + i) * 3 + a];
+      if (x_aos) d.x[off + a * Npad + i] = x_aos[((size_t)k * N + i) * 3 + a];   // re-wrapped by the list build that follows
       if (v_aos) d.v[off + a * Npad + i] = v_aos[((size_t)k * N + i) * 3 + a];
     }
   if (threadIdx.x == 0) {
@@ -767,7 +874,7 @@ __global__ void k_gather_state(Dev d, double* x_aos, double* v_aos, double* box,
   const size_t off = (size_t)c * 3 * Npad;
   for (int i = threadIdx.x; i < N; i += blockDim.x)
     for (int a = 0; a < 3; a++) {
-      if (x_aos) x_aos[((size_t)k * N + i) * 3 + a] = d.x[off + a * Npad + i];
+      if (x_aos) x_aos[((size_t)k * N + i) * 3 + a] = wrapg(d.x[off + a * Npad + i], d.box[c]);
       if (v_aos) v_aos[((size_t)k * N + i) * 3 + a] = d.v[off + a * Npad + i];
     }
   if (threadIdx.x == 0) {
@@ -860,14 +967,17 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     const double rl = d.rc + d.skin;
     int maxnb = (int)(4.18879 * rl * rl * rl * 1.6) + 16;
     if (maxnb > N - 1) maxnb = N - 1;
-    d.maxq = (maxnb + 3) / 4; if (d.maxq < 1) d.maxq = 1;
+    if (maxnb < 1) maxnb = 1;
+    d.maxnb = maxnb;
+    d.maxq = (maxnb + 3) / 4 + 16;          // + padding of up to 27 image groups to whole quads
   }
-  h->threads = N <= 256 ? 256 : 512;     // 512 threads keep the cycle kernel at 128 registers without spills
+  h->threads = N <= 256 ? 256 : (N <= 512 ? 512 : 1024);   // 64 registers/thread: 32 warps per SM hide the FP64 latency
   h->smem = smem_bytes(d.Npad);
   if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
   const size_t per = (size_t)nrep * 3 * d.Npad;
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, per);
-  DA(d.list, (size_t)nrep * d.maxq * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad);
+  DA(d.list, (size_t)nrep * d.maxq * d.Npad); DA(d.qcode, (size_t)nrep * d.maxq * d.Npad);
+  DA(d.ltmp, (size_t)nrep * d.maxnb * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad); DA(d.micmode, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
   DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep);
@@ -887,7 +997,8 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   cudaError_t e = cudaSuccess;
   const int sm = (int)h->smem;
   if (h->threads == 256) { e = cudaFuncSetAttribute(k_cycle<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
-  else { e = cudaFuncSetAttribute(k_cycle<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
+  else if (h->threads == 512) { e = cudaFuncSetAttribute(k_cycle<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
+  else { e = cudaFuncSetAttribute(k_cycle<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
   if (e != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "cudaFuncSetAttribute(smem=%zu): %s", h->smem, cudaGetErrorString(e)); }
   *out = h;
   return NM_OK;
@@ -923,14 +1034,15 @@ static int check_status(nm_engine* h) {
   CK(cudaStreamSynchronize(h->stream));
   for (int c = 0; c < h->d.nrep; c++) {
     if (st[c] & ST_BOX) return fail(NM_EBOX, "configuration %d: box side below 2*rc (minimum image invalid)", c);
-    if (st[c] & ST_NEIGH) return fail(NM_ENEIGH, "configuration %d: neighbour list capacity (%d) exceeded", c, h->d.maxq * 4);
+    if (st[c] & ST_NEIGH) return fail(NM_ENEIGH, "configuration %d: neighbour list capacity (%d) exceeded", c, h->d.maxnb);
   }
   return NM_OK;
 }
 
 static int launch_eval(nm_engine* h, double* pe, double* w, double* f_aos, long long* np_) {
   if (h->threads == 256) k_eval<256><<<h->d.nrep, 256, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
-  else k_eval<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
+  else if (h->threads == 512) k_eval<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
+  else k_eval<1024><<<h->d.nrep, 1024, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
   h->launches++;
   CK(cudaGetLastError());
   return NM_OK;
@@ -1008,7 +1120,8 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   if (!h->have_state || !h->have_labels) return fail(NM_ESTATE, "nm_run_cycle: state and labels must be uploaded first");
   CK(cudaSetDevice(h->cfg.device));
   if (h->threads == 256) k_cycle<256><<<h->d.nrep, 256, h->smem, h->stream>>>(h->d, (long long)cycle);
-  else k_cycle<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, (long long)cycle);
+  else if (h->threads == 512) k_cycle<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, (long long)cycle);
+  else k_cycle<1024><<<h->d.nrep, 1024, h->smem, h->stream>>>(h->d, (long long)cycle);
   h->launches++;
   CK(cudaGetLastError());
   h->have_thermo = true;

@@ -45,6 +45,7 @@ def main():
         print("cycle %d: %.1f ms  atom-steps/s %.3e  sweeps/s %.3e  pair-flops %.2f TF/s  builds %d evals %d  listpairs/inpairs %.2f swaps %d  <ah> %.2f <av> %.2f <ap> %.2f" % (
             cyc, dt * 1e3, ct["hmc_atom_steps"] / dt, ct["sweeps"] / dt, flops / dt / 1e12, ct["list_builds"], ct["force_evals"],
             ct["list_pairs"] / max(1, ct["pairs_force"] + ct["pairs_full"]), sw, th[:, 17].mean(), th[:, 16].mean(), th[:, 15].mean()))
+        print("   clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
     print("T col0 thermo:", np.round(th[:nt, :6], 3)[::max(1, nt // 4)])
 
 main()
