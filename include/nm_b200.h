@@ -55,7 +55,7 @@ enum nm_thermo_col {
 
 /* counters returned by nm_get_counters (uint64 each, summed over local replicas
  * since nm_create or the last nm_reset_counters) */
-#define NM_COUNTER_WIDTH 16
+#define NM_COUNTER_WIDTH 20
 enum nm_counter_col {
   NM_CT_SWEEPS = 0,        /* move_mc calls (lammps_remcmc.py:677-679)            */
   NM_CT_HMC_MOVES,         /* hamiltonian_mc calls                                */
@@ -72,6 +72,10 @@ enum nm_counter_col {
   NM_CT_CLK_EVAL,          /* SM clocks spent in force evaluations (summed over CTAs) */
   NM_CT_CLK_BUILD,         /* SM clocks spent in list builds                      */
   NM_CT_CLK_TOTAL,         /* SM clocks of the cycle kernels                      */
+  NM_CT_OUTER_BUILDS,      /* outer (cell-search) list builds                     */
+  NM_CT_CLK_OUTER,         /* SM clocks in outer builds                           */
+  NM_CT_CLK_INNER,         /* SM clocks in inner builds                           */
+  NM_CT_CLK_VEL,           /* SM clocks in the HMC velocity draw                  */
   NM_CT_RESERVED
 };
 
@@ -98,7 +102,8 @@ typedef struct nm_config {
   double   lat_scale;       /* LAT[EL][1] (1.122): displacement scale factor               */
   double   mass;            /* MASS[EL]                                                    */
   double   rc;              /* lj/cut cutoff (2.5); epsilon = sigma = 1                    */
-  double   skin;            /* Verlet-list skin; <= 0 selects the default                  */
+  double   skin;            /* inner Verlet-list skin; <= 0 selects the default (0.3)      */
+  double   skin_outer;      /* extra radius of the outer list; <= 0 selects the default (0.8) */
   uint64_t seed;            /* counter-based RNG seed (reference: SEED = 256)              */
   void*    stream;          /* cudaStream_t to launch on; NULL = engine-owned stream       */
 } nm_config;

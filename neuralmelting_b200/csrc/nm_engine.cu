@@ -28,15 +28,20 @@ constexpr int ST_BOX = 1, ST_NEIGH = 2;  // status bits
 
 // ------------------------------------------------------------------ device-side engine description
 struct Dev {
-  int N, Npad, nrep, nrep_global, rep_offset, nt, maxq, maxnb;   // list capacity in quads / scratch entries
+  int N, Npad, nrep, nrep_global, rep_offset, nt, maxq, maxqo, maxnbo;   // inner / outer list capacity in quads, outer scratch entries
   int nstps, mod, bulk, text_rounding;
-  double ppos, pvol, lat, mass, rc, skin;
+  double ppos, pvol, lat, mass, rc, skin, oskin;
   uint32_t seed_lo, seed_hi;
   // per configuration
   double *x, *v, *f, *xs, *vs, *fs, *x0;   // [nrep][3][Npad]
   ushort4* list;                           // [nrep][maxq][Npad]  neighbour quads, grouped by periodic image
   uint8_t* qcode;                          // [nrep][maxq][Npad]  image code (0..26) of each quad
-  uint32_t* ltmp;                          // [nrep][maxnb][Npad] build scratch: j | code << 16 in discovery order
+  uint32_t* ltmp;                          // [nrep][maxnbo][Npad] outer-build scratch: j | code << 16 in discovery order
+  ushort4* olist;                          // [nrep][maxqo][Npad] OUTER list (radius rc+skin+oskin), same grouped format
+  uint8_t* ocode;                          // [nrep][maxqo][Npad]
+  uint16_t* onq;                           // [nrep][Npad]
+  double* x0o;                             // [nrep][3][Npad] fractional coordinates at the last outer build
+  double* L0o;                             // [nrep] box at the last outer build
   uint16_t* nnb;                           // [nrep][Npad]        number of quads of atom i
   int* micmode;                            // [nrep] 1: box < 2(rc+skin) at build, images resolved per pair
   double *box, *pe, *w, *ke, *L0;          // [nrep]
@@ -65,6 +70,8 @@ struct Ctx {
   // global views of this configuration
   double *gx, *gv, *gf, *gxs, *gvs, *gfs, *gx0;
   ushort4* list; uint8_t* qcode; uint32_t* ltmp; uint16_t* nnb;
+  ushort4* olist; uint8_t* ocode; uint16_t* onq; double* gx0o;
+  double L0o, thro2;            // outer list: build box and squared displacement budget
   double* sht;                  // shared: 27 image shift vectors (k*L) for the current box
   int mic;                      // minimum image per pair (small boxes) instead of stored image codes
   unsigned long long ct[NM_COUNTER_WIDTH];   // meaningful on thread 0 only
@@ -101,7 +108,12 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off; cx.gx0 = d.x0 + off;
   cx.list = d.list + (size_t)c * d.maxq * d.Npad;
   cx.qcode = d.qcode + (size_t)c * d.maxq * d.Npad;
-  cx.ltmp = d.ltmp + (size_t)c * d.maxnb * d.Npad;
+  cx.ltmp = d.ltmp + (size_t)c * ((d.maxnbo + 3) & ~3) * d.Npad;
+  cx.olist = d.olist + (size_t)c * d.maxqo * d.Npad;
+  cx.ocode = d.ocode + (size_t)c * d.maxqo * d.Npad;
+  cx.onq = d.onq + (size_t)c * d.Npad;
+  cx.gx0o = d.x0o + off;
+  cx.L0o = d.L0o[c];
   cx.nnb = d.nnb + (size_t)c * d.Npad;
   cx.mic = d.micmode[c];
   cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.Lsave = cx.L; cx.list_pairs = d.list_pairs[c];
@@ -110,18 +122,31 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; }
 }
 
-// displacement budget of the current list for box L: s*(rl - 2u) >= rc, s = L/L0
+// displacement budgets for box L (s = L/L0): inner list complete while s*(rl - 2u) >= rc; the outer list can
+// regenerate a complete inner list while s*(rlo - 2u) >= rl
 __device__ __forceinline__ void update_thr(const Dev& d, Ctx& cx) {
-  if (cx.L0 <= 0.0) { cx.thr2 = -1.0; return; }
-  const double s = cx.L / cx.L0, rl = d.rc + d.skin;
-  const double thr = 0.5 * (rl - d.rc / s) * (1.0 - 1e-9);
-  cx.thr2 = thr > 0.0 ? thr * thr : -1.0;
+  const double rl = d.rc + d.skin, rlo = rl + d.oskin;
+  if (cx.L0 <= 0.0) cx.thr2 = -1.0;
+  else {
+    const double s = cx.L / cx.L0, thr = 0.5 * (rl - d.rc / s) * (1.0 - 1e-9);
+    cx.thr2 = thr > 0.0 ? thr * thr : -1.0;
+  }
+  if (cx.L0o <= 0.0) cx.thro2 = -1.0;
+  else {
+    const double s = cx.L / cx.L0o, thr = 0.5 * (rlo - rl * (1.0 + 1e-4) / s) * (1.0 - 1e-9);
+    cx.thro2 = thr > 0.0 ? thr * thr : -1.0;
+  }
 }
-// squared displacement of (x,y,z) from the list reference of atom i, in build-box length units
+// squared displacement of (x,y,z) from the inner / outer list reference of atom i, in build-box length units
 __device__ __forceinline__ double disp2(const Ctx& cx, int i, double x, double y, double z, double invL) {
   double ux = x * invL - cx.gx0[i], uy = y * invL - cx.gx0[cx.Npad + i], uz = z * invL - cx.gx0[2 * cx.Npad + i];
   ux -= rint(ux); uy -= rint(uy); uz -= rint(uz);
   return (ux * ux + uy * uy + uz * uz) * cx.L0 * cx.L0;
+}
+__device__ __forceinline__ double disp2o(const Ctx& cx, int i, double x, double y, double z, double invL) {
+  double ux = x * invL - cx.gx0o[i], uy = y * invL - cx.gx0o[cx.Npad + i], uz = z * invL - cx.gx0o[2 * cx.Npad + i];
+  ux -= rint(ux); uy -= rint(uy); uz -= rint(uz);
+  return (ux * ux + uy * uy + uz * uz) * cx.L0o * cx.L0o;
 }
 
 // positions global -> shared, plus the far-away dummy atom that pads the list. Positions are CONTINUOUS between
@@ -139,24 +164,24 @@ __device__ void store_positions(Ctx& cx) {
   }
 }
 
-// ------------------------------------------------------------------ Verlet list build (cell binned, deterministic)
-// Produces, per atom i, neighbour quads GROUPED BY PERIODIC IMAGE: every quad carries one image code
-// (kx+1)*9 + (ky+1)*3 + (kz+1), k = rint((x_i - x_j)/L), so the force loop subtracts the image shift once per
-// quad from x_i and needs no per-pair minimum-image arithmetic. Groups are padded to whole quads with the
-// far-away dummy atom N. Atoms are re-wrapped into [0,L) here (and only here); the saved copy used for move
-// reverts is shifted by the same lattice vector so that a revert stays consistent with the new list.
-__device__ void build_list(const Dev& d, Ctx& cx) {
+// ------------------------------------------------------------------ two-level Verlet lists (deterministic)
+// OUTER list (radius rlo = rc + skin + oskin): cell-binned search on the FP32 pipe, rebuilt rarely. Per atom i it
+// holds neighbour quads GROUPED BY PERIODIC IMAGE: every quad carries one image code (kx+1)*9+(ky+1)*3+(kz+1),
+// k = rint((x_i - x_j)/L), groups padded to whole quads with the far-away dummy atom N.
+// INNER list (radius rl = rc + skin): the subset of the outer list currently within rl, regenerated often by a
+// single pass over the outer quads (it inherits the grouping). The force loop walks the inner list and subtracts
+// the image shift once per quad -- no per-pair minimum-image arithmetic.
+// Atoms are re-wrapped into [0,L) at outer builds only; the saved copy used for move reverts is shifted by the
+// same lattice vector so that a revert stays consistent with the stored image codes.
+__device__ void build_outer(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
-  const double L = cx.L, rl = d.rc + d.skin, rl2 = rl * rl, invL = 1.0 / L;
-  int nc = (int)floor(L / (rl * (1.0 + 1e-4)));
+  const double L = cx.L, rlo = d.rc + d.skin + d.oskin, invL = 1.0 / L;
+  int nc = (int)floor(L / (rlo * (1.0 + 1e-4)));
   if (nc > NCMAX) nc = NCMAX;
   if (nc < 3) nc = 1;
   const int ncell = nc * nc * nc;
-  const long long t_build0 = clock64();
+  cx.mic = L < 2.0 * rlo * (1.0 + 1e-3);    // small box: the nearest image of a listed pair may change between builds
   __syncthreads();
-  // wrap + float32 fractional copies: the neighbour search runs entirely on the FP32 pipe. A pair enters the list
-  // when its float32 distance is below rl*(1+margin); the margin covers the float32 rounding of the fractional
-  // coordinates (<= 2^-24 each, < 4e-6 relative on r^2 at r ~ rl), so the list is a superset of {r < rl}.
   for (int i = tid; i < N; i += nthr) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -206,17 +231,24 @@ __device__ void build_list(const Dev& d, Ctx& cx) {
     }
     __syncthreads();
   }
-  uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
-  const float rl2f = (float)(rl2 * invL * invL * (1.0 + 2e-5));
+  // a pair enters the list when its float32 distance is below rlo*(1+margin); the margin covers the float32 rounding
+  // of the fractional coordinates (<= 2^-24 each, < 4e-6 relative on r^2), so the list is a superset of {r < rlo}.
+  // Build-side arrays (scratch, outer list, outer codes) are ROW-MAJOR PER ATOM so that the owning thread streams
+  // them with 16-byte accesses. With box >= 2 rlo the image of a neighbour along one axis is either 0 or one fixed
+  // sign per atom (-1 for atoms in the lower half of the box, +1 in the upper half): at most 8 image groups,
+  // indexed g = (kx != 0) | (ky != 0) << 1 | (kz != 0) << 2, counted in one packed 64-bit register.
+  const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
   const float magic = 12582912.f;          // 1.5 * 2^23: (x + magic) - magic = rint(x) for |x| < 2^22
-  double tot = 0.0; int over = 0;
+  const bool grouped = !cx.mic;
+  const int trow_len = (d.maxnbo + 3) & ~3;
+  int over = 0;
   for (int i = tid; i < N; i += nthr) {
     const float4 pi = cx.sf[i];
-    unsigned char c27[27];
-#pragma unroll
-    for (int c = 0; c < 27; c++) c27[c] = 0;
+    uint32_t* trow = cx.ltmp + (size_t)i * trow_len;
+    unsigned long long gcnt_lo = 0ull, gcnt_hi = 0ull;   // 8 image-group counters, 16 bits each
     int cnt = 0;
-    auto test = [&](int j) {                 // pass A: discovery order -> scratch, count per image code
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    auto test = [&](int j) {                 // pass A: hits in discovery order -> scratch row, count per image group
       const float4 pj = cx.sf[j];
       float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
       const float kx = __fadd_rn(__fadd_rn(dx, magic), -magic), ky = __fadd_rn(__fadd_rn(dy, magic), -magic),
@@ -224,8 +256,14 @@ __device__ void build_list(const Dev& d, Ctx& cx) {
       dx -= kx; dy -= ky; dz -= kz;
       const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
       if (r2 < rl2f && j != i) {
-        const int code = (int)kx * 9 + (int)ky * 3 + (int)kz + 13;
-        if (cnt < d.maxnb) { cx.ltmp[(size_t)cnt * Npad + i] = (uint32_t)j | ((uint32_t)code << 16); c27[code]++; }
+        if (cnt < d.maxnbo) {
+          const int g = grouped ? ((kx != 0.f) | ((ky != 0.f) << 1) | ((kz != 0.f) << 2)) : 0;
+          const uint32_t en = (uint32_t)j | ((uint32_t)g << 16);
+          const int slot = cnt & 3;
+          b0 = slot == 0 ? en : b0; b1 = slot == 1 ? en : b1; b2 = slot == 2 ? en : b2; b3 = slot == 3 ? en : b3;
+          if (slot == 3) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
+          if (g < 4) gcnt_lo += 1ull << (16 * g); else gcnt_hi += 1ull << (16 * (g - 4));
+        }
         cnt++;
       }
     };
@@ -239,26 +277,98 @@ __device__ void build_list(const Dev& d, Ctx& cx) {
         for (int p = s; p < en; p++) test(cx.cell_atoms[p]);
       }
     }
-    if (cnt > d.maxnb) { over = 1; cnt = d.maxnb; }
-    // group offsets (in entries, each group padded to a whole quad)
-    unsigned short cur[27];
-    int nq = 0;
+    if (cnt > d.maxnbo) { over = 1; cnt = d.maxnbo; }
+    if (cnt & 3) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
+    // pass B: one sweep of the scratch row per non-empty image group; quads are written whole (8 bytes)
+    ushort4* orow = cx.olist + (size_t)i * d.maxqo;
+    uint8_t* crow = cx.ocode + (size_t)i * d.maxqo;
+    const int sx = pi.x < 0.5f ? -1 : 1, sy = pi.y < 0.5f ? -1 : 1, sz = pi.z < 0.5f ? -1 : 1;
+    int q = 0;
+    for (int g = 0; g < 8; g++) {
+      const int ng = (int)(((g < 4 ? gcnt_lo >> (16 * g) : gcnt_hi >> (16 * (g - 4)))) & 0xffffull);
+      if (ng == 0) continue;
+      if (q + ((ng + 3) >> 2) > d.maxqo) { over = 1; break; }
+      const int code = 13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz;
+      unsigned short a0 = (unsigned short)N, a1 = a0, a2 = a0, a3 = a0;
+      int fill = 0;
+      for (int t = 0; t < cnt; t += 4) {
+        const uint4 e4 = *reinterpret_cast<const uint4*>(trow + t);
+        const uint32_t ee[4] = { e4.x, e4.y, e4.z, e4.w };
 #pragma unroll
-    for (int c = 0; c < 27; c++) { cur[c] = (unsigned short)(nq * 4); nq += (c27[c] + 3) >> 2; }
-    if (nq > d.maxq) { over = 1; nq = d.maxq; }
-    for (int c = 0, q = 0; c < 27 && q < nq; c++) {
-      const int gq = (c27[c] + 3) >> 2;
-      for (int g = 0; g < gq && q < nq; g++, q++) {
-        cx.qcode[(size_t)q * Npad + i] = (uint8_t)c;
-        cx.list[(size_t)q * Npad + i] = make_ushort4((unsigned short)N, (unsigned short)N, (unsigned short)N, (unsigned short)N);
+        for (int u = 0; u < 4; u++) {
+          if (t + u < cnt && (int)(ee[u] >> 16) == g) {
+            const unsigned short j = (unsigned short)(ee[u] & 0xffffu);
+            a0 = fill == 0 ? j : a0; a1 = fill == 1 ? j : a1; a2 = fill == 2 ? j : a2; a3 = fill == 3 ? j : a3;
+            if (++fill == 4) {
+              orow[q] = make_ushort4(a0, a1, a2, a3); crow[q] = (uint8_t)code; q++;
+              fill = 0; a0 = a1 = a2 = a3 = (unsigned short)N;
+            }
+          }
+        }
       }
+      if (fill) { orow[q] = make_ushort4(a0, a1, a2, a3); crow[q] = (uint8_t)code; q++; }
     }
-    for (int t = 0; t < cnt; t++) {          // pass B: counting sort by image code
-      const uint32_t en = cx.ltmp[(size_t)t * Npad + i];
-      const int c = en >> 16, k = cur[c]++;
-      if ((k >> 2) < nq) l16[((size_t)(k >> 2) * Npad + i) * 4 + (k & 3)] = (uint16_t)(en & 0xffffu);
+    cx.onq[i] = (uint16_t)q;
+    cx.gx0o[i] = cx.sp[3 * i] * invL; cx.gx0o[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0o[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+  }
+  if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
+  cx.L0o = L;
+  update_thr(d, cx);
+  if (tid == 0) cx.ct[NM_CT_OUTER_BUILDS]++;
+}
+
+// inner list = the outer entries currently within rl (float32 test with the stored image; minimum image in MIC mode).
+// The owning thread streams its outer row and emits whole 8-byte quads into the [quad][atom] layout the force loop reads.
+__device__ void build_inner(const Dev& d, Ctx& cx) {
+  const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
+  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
+  __syncthreads();
+  for (int i = tid; i < Npad; i += nthr)
+    cx.sf[i] = i < N ? make_float4((float)(cx.sp[3 * i] * invL), (float)(cx.sp[3 * i + 1] * invL), (float)(cx.sp[3 * i + 2] * invL), 0.f)
+                     : make_float4(1e6f, 1e6f, 1e6f, 0.f);
+  __syncthreads();
+  const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
+  const float magic = 12582912.f;
+  const bool mic = cx.mic;
+  double tot = 0.0; int over = 0;
+  for (int i = tid; i < N; i += nthr) {
+    const float4 pi = cx.sf[i];
+    const int nqo = cx.onq[i];
+    const ushort4* orow = cx.olist + (size_t)i * d.maxqo;
+    const uint8_t* crow = cx.ocode + (size_t)i * d.maxqo;
+    unsigned short a0 = (unsigned short)N, a1 = a0, a2 = a0, a3 = a0;
+    int oq = 0, fill = 0, curcode = 13, cnt = 0;
+    auto flush = [&]() {
+      if (oq < d.maxq) { cx.list[(size_t)oq * Npad + i] = make_ushort4(a0, a1, a2, a3); cx.qcode[(size_t)oq * Npad + i] = (uint8_t)curcode; }
+      else over = 1;
+      oq++; fill = 0; a0 = a1 = a2 = a3 = (unsigned short)N;
+    };
+    ushort4 e4 = nqo > 0 ? orow[0] : make_ushort4(0, 0, 0, 0);
+    int code = nqo > 0 ? crow[0] : 13;
+    for (int q = 0; q < nqo; q++) {
+      const ushort4 n4 = (q + 1 < nqo) ? orow[q + 1] : e4;
+      const int ncode = (q + 1 < nqo) ? crow[q + 1] : 13;
+      const float sx = (float)(code / 9 - 1), sy = (float)((code / 3) % 3 - 1), sz = (float)(code % 3 - 1);
+      if (code != curcode) { if (fill) flush(); curcode = code; }
+      const int jj[4] = { e4.x, e4.y, e4.z, e4.w };
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const float4 pj = cx.sf[jj[t]];
+        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        if (mic) { dx -= __fadd_rn(__fadd_rn(dx, magic), -magic); dy -= __fadd_rn(__fadd_rn(dy, magic), -magic); dz -= __fadd_rn(__fadd_rn(dz, magic), -magic); }
+        else { dx -= sx; dy -= sy; dz -= sz; }
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (r2 < rl2f) {
+          const unsigned short j = (unsigned short)jj[t];
+          a0 = fill == 0 ? j : a0; a1 = fill == 1 ? j : a1; a2 = fill == 2 ? j : a2; a3 = fill == 3 ? j : a3;
+          cnt++;
+          if (++fill == 4) flush();
+        }
+      }
+      e4 = n4; code = ncode;
     }
-    cx.nnb[i] = (uint16_t)nq;
+    if (fill) flush();
+    cx.nnb[i] = (uint16_t)min(oq, d.maxq);
     tot += cnt;
     cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
   }
@@ -267,9 +377,21 @@ __device__ void build_list(const Dev& d, Ctx& cx) {
   cx.list_pairs = 0.5 * r[0];
   if (r[1] > 0.0) cx.status |= ST_NEIGH;
   cx.L0 = L;
-  cx.mic = L < 2.0 * rl * (1.0 + 1e-3);     // small box: the nearest image of a listed pair may change between builds
   update_thr(d, cx);
-  if (tid == 0) { cx.ct[NM_CT_LIST_BUILDS]++; cx.ct[NM_CT_CLK_BUILD] += (unsigned long long)(clock64() - t_build0); }
+}
+
+// (re)build: make sure the outer list can still supply every pair within rl, then regenerate the inner list
+__device__ void build_list(const Dev& d, Ctx& cx) {
+  const long long t_build0 = clock64();
+  int flag = cx.thro2 < 0.0;
+  if (!flag) {
+    const double invL = 1.0 / cx.L;
+    for (int i = threadIdx.x; i < cx.N; i += blockDim.x)
+      flag |= disp2o(cx, i, cx.sp[3 * i], cx.sp[3 * i + 1], cx.sp[3 * i + 2], invL) > cx.thro2;
+  }
+  if (__syncthreads_or(flag)) { const long long t0 = clock64(); build_outer(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t0); }
+  { const long long t0 = clock64(); build_inner(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_INNER] += (unsigned long long)(clock64() - t0); }
+  if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; cx.ct[NM_CT_CLK_BUILD] += (unsigned long long)(clock64() - t_build0); }
 }
 
 // barrier after a position update; rebuilds the list if any thread saw its budget exceeded
@@ -573,7 +695,9 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
 // ------------------------------------------------------------------ a-3 / a-5 hamiltonian_mc (lammps_remcmc.py:598-640)
 __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double t_vel, double dts, Energy& en, double* cnt) {
   const int N = cx.N, Npad = cx.Npad;
+  const long long t_vel0 = clock64();
   const double ke0 = velocity_create(d, cx, r, t_vel);
+  if (threadIdx.x == 0) cx.ct[NM_CT_CLK_VEL] += (unsigned long long)(clock64() - t_vel0);
   save_xf(cx, true);
   const double dt = d.text_rounding ? round6(dts) : dts;                        // 'timestep %f'
   const double dtf = 0.5 * dt / d.mass;
@@ -721,7 +845,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
     }
   }
   if (threadIdx.x == 0) {
-    d.pe[cx.c] = o[0]; d.w[cx.c] = o[1]; d.ke[cx.c] = 0.5 * d.mass * t[0]; d.L0[cx.c] = cx.L0; d.micmode[cx.c] = cx.mic; d.list_pairs[cx.c] = cx.list_pairs;
+    d.pe[cx.c] = o[0]; d.w[cx.c] = o[1]; d.ke[cx.c] = 0.5 * d.mass * t[0]; d.L0[cx.c] = cx.L0; d.L0o[cx.c] = cx.L0o; d.micmode[cx.c] = cx.mic; d.list_pairs[cx.c] = cx.list_pairs;
     if (pe_out) pe_out[slot] = o[0];
     if (w_out) w_out[slot] = o[1];
     if (npairs_out) npairs_out[slot] = (long long)o[2];
@@ -775,7 +899,7 @@ k_cycle(Dev d, long long cycle) {
       const float a = (float)cnt[2 * k + 1] / (float)cnt[2 * k];        // float32 ratio, nan_to_num (0/0 -> 0)
       th[NM_TH_AP + k] = isnan(a) ? 0.0 : (double)a;
     }
-    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs;
+    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.L0o[c] = cx.L0o; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs;
     if (cx.status) d.status[c] |= cx.status;
     cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
     cx.ct[NM_CT_CLK_TOTAL] += (unsigned long long)(clock64() - t_cycle0);
@@ -866,7 +990,7 @@ __global__ void k_scatter_state(Dev d, const double* x_aos, const double* v_aos,
     if (dx) d.step[3 * c] = dx[k];
     if (dv) d.step[3 * c + 1] = dv[k];
     if (dt) d.step[3 * c + 2] = dt[k];
-    if (x_aos || box) d.L0[c] = -1.0;      // new configuration: the old list is meaningless
+    if (x_aos || box) { d.L0[c] = -1.0; d.L0o[c] = -1.0; }   // new configuration: the old lists are meaningless
   }
 }
 __global__ void k_gather_state(Dev d, double* x_aos, double* v_aos, double* box, double* dx, double* dv, double* dt) {
@@ -961,15 +1085,21 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   d.nstps = cfg->nstps; d.mod = cfg->mod; d.bulk = cfg->bulk_move; d.text_rounding = cfg->text_rounding;
   d.ppos = cfg->ppos; d.pvol = cfg->pvol; d.lat = cfg->lat_scale; d.mass = cfg->mass; d.rc = cfg->rc;
   d.skin = cfg->skin > 0 ? cfg->skin : 0.3;
+  d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 0.8;
   d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);
   {
-    // list capacity: neighbours inside rc+skin at the densest state we expect (rho* 1.6) plus slack
-    const double rl = d.rc + d.skin;
-    int maxnb = (int)(4.18879 * rl * rl * rl * 1.6) + 16;
+    // list capacities: neighbours inside the list radius at the densest state we expect (rho* 1.6) plus slack,
+    // plus padding of the image groups (at most 8 per atom when the box is >= 2 rlo) to whole quads
+    const double rl = d.rc + d.skin, rlo = rl + d.oskin;
+    int maxnb = (int)(4.18879 * rl * rl * rl * 1.6) + 16, maxnbo = (int)(4.18879 * rlo * rlo * rlo * 1.6) + 16;
     if (maxnb > N - 1) maxnb = N - 1;
+    if (maxnbo > N - 1) maxnbo = N - 1;
+    if (maxnb > maxnbo) maxnb = maxnbo;
     if (maxnb < 1) maxnb = 1;
-    d.maxnb = maxnb;
-    d.maxq = (maxnb + 3) / 4 + 16;          // + padding of up to 27 image groups to whole quads
+    if (maxnbo < 1) maxnbo = 1;
+    d.maxnbo = maxnbo;
+    d.maxq = (maxnb + 3) / 4 + 8;
+    d.maxqo = ((maxnbo + 3) / 4 + 8 + 1) & ~1;
   }
   h->threads = N <= 256 ? 256 : (N <= 512 ? 512 : 1024);   // 64 registers/thread: 32 warps per SM hide the FP64 latency
   h->smem = smem_bytes(d.Npad);
@@ -977,7 +1107,9 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   const size_t per = (size_t)nrep * 3 * d.Npad;
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, per);
   DA(d.list, (size_t)nrep * d.maxq * d.Npad); DA(d.qcode, (size_t)nrep * d.maxq * d.Npad);
-  DA(d.ltmp, (size_t)nrep * d.maxnb * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad); DA(d.micmode, nrep);
+  DA(d.ltmp, (size_t)nrep * ((d.maxnbo + 3) & ~3) * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad); DA(d.micmode, nrep);
+  DA(d.olist, (size_t)nrep * d.maxqo * d.Npad); DA(d.ocode, (size_t)nrep * d.maxqo * d.Npad); DA(d.onq, (size_t)nrep * d.Npad);
+  DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
   DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep);
@@ -992,6 +1124,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     cudaError_t e1 = cudaMemcpy(d.cfg_slot, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
     cudaError_t e2 = cudaMemcpy(d.slot_cfg, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
     cudaError_t e3 = cudaMemcpy(d.L0, neg.data(), sizeof(double) * nrep, cudaMemcpyHostToDevice);
+    if (e3 == cudaSuccess) e3 = cudaMemcpy(d.L0o, neg.data(), sizeof(double) * nrep, cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "nm_create: init copy failed"); }
   }
   cudaError_t e = cudaSuccess;
@@ -1034,7 +1167,7 @@ static int check_status(nm_engine* h) {
   CK(cudaStreamSynchronize(h->stream));
   for (int c = 0; c < h->d.nrep; c++) {
     if (st[c] & ST_BOX) return fail(NM_EBOX, "configuration %d: box side below 2*rc (minimum image invalid)", c);
-    if (st[c] & ST_NEIGH) return fail(NM_ENEIGH, "configuration %d: neighbour list capacity (%d) exceeded", c, h->d.maxnb);
+    if (st[c] & ST_NEIGH) return fail(NM_ENEIGH, "configuration %d: neighbour list capacity (%d inner quads / %d outer entries) exceeded", c, h->d.maxq, h->d.maxnbo);
   }
   return NM_OK;
 }

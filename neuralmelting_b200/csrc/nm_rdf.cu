@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(T) k_rdf(RdfParams p) {
 
 }  // namespace nmrdf
 
-static thread_local char g_rdf_err[512] = "";
+
 extern "C" const char* nm_last_error(void);
 // error text is routed through the engine's thread-local buffer
 extern int nm_fail_msg(int code, const char* fmt, ...);
@@ -179,6 +179,6 @@ done:
   else if (!dev_ptrs) { /* already synchronised */ }
   if (d_thr) { cudaStreamSynchronize(st); cudaFree(d_thr); }
   if (!dev_ptrs) { if (d_pos) cudaFree(d_pos); if (d_box) cudaFree(d_box); if (d_cnt) cudaFree(d_cnt); }
-  (void)g_rdf_err;
+
   return rc;
 }

@@ -16,10 +16,10 @@ LIB_PATH = os.path.join(_HERE, "libnm_b200.so")
 THERMO_WIDTH = 18
 THERMO_COLS = ("temp", "pe", "ke", "virial", "box", "vol", "dx", "dv", "dt",
                "ntp", "nap", "ntv", "nav", "nth", "nah", "ap", "av", "ah")
-COUNTER_WIDTH = 16
+COUNTER_WIDTH = 20
 COUNTER_COLS = ("sweeps", "hmc_moves", "hmc_atom_steps", "vmc_moves", "pmc_moves", "pmc_trials",
                 "force_evals", "pairs_force", "pairs_full", "pairs_delta", "list_builds", "list_pairs",
-                "clk_eval", "clk_build", "clk_total", "reserved")
+                "clk_eval", "clk_build", "clk_total", "outer_builds", "clk_outer", "clk_inner", "clk_vel", "reserved")
 
 NM_OK, NM_EINVAL, NM_ENODEV, NM_ECUDA, NM_ENOMEM, NM_EBOX, NM_ENEIGH, NM_ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 
@@ -36,7 +36,7 @@ class NmConfig(C.Structure):
                 ("nt", C.c_int32), ("precision", C.c_int32), ("nstps", C.c_int32), ("mod", C.c_int32),
                 ("bulk_move", C.c_int32), ("text_rounding", C.c_int32),
                 ("ppos", C.c_double), ("pvol", C.c_double), ("lat_scale", C.c_double),
-                ("mass", C.c_double), ("rc", C.c_double), ("skin", C.c_double),
+                ("mass", C.c_double), ("rc", C.c_double), ("skin", C.c_double), ("skin_outer", C.c_double),
                 ("seed", C.c_uint64), ("stream", C.c_void_p)]
 
 
@@ -113,7 +113,7 @@ class Engine:
     """
 
     def __init__(self, natoms, n_rep, nt, n_rep_global=None, rep_offset=0, device=0, nstps=8, mod=128,
-                 bulk_move=False, ppos=0.125, pvol=0.125, lat_scale=1.122, mass=1.0, rc=2.5, skin=0.0,
+                 bulk_move=False, ppos=0.125, pvol=0.125, lat_scale=1.122, mass=1.0, rc=2.5, skin=0.0, skin_outer=0.0,
                  seed=256, text_rounding=True, precision=64, stream=None):
         L = load_library()
         self.natoms, self.n_rep, self.nt = int(natoms), int(n_rep), int(nt)
@@ -122,7 +122,7 @@ class Engine:
         self.mod, self.nstps = int(mod), int(nstps)
         cfg = NmConfig(C.sizeof(NmConfig), device, natoms, n_rep, self.n_rep_global, rep_offset, nt, precision,
                        nstps, mod, int(bool(bulk_move)), int(bool(text_rounding)), ppos, pvol, lat_scale, mass, rc,
-                       skin, seed, stream)
+                       skin, skin_outer, seed, stream)
         self._h = C.c_void_p()
         _check(L.nm_create(C.byref(cfg), C.byref(self._h)))
         self._L = L

@@ -24,12 +24,13 @@ def main():
     ncyc = int(sys.argv[4]) if len(sys.argv) > 4 else 3
     bulk = int(sys.argv[5]) if len(sys.argv) > 5 else 1
     skin = float(sys.argv[6]) if len(sys.argv) > 6 else 0.0
+    oskin = float(sys.argv[7]) if len(sys.argv) > 7 else 0.0
     n, x, box, et, pf, tt = grid(n_side, np_, nt)
     ns = np_ * nt
     for prec in (64, 32):
         fl, ms = nm.measure_fma_peak(0, prec)
         print("fma peak fp%d: %.2f TFLOP/s (%.3f ms)" % (prec, fl / 1e12, ms))
-    eng = nm.Engine(natoms=n, n_rep=ns, nt=nt, bulk_move=bool(bulk), skin=skin)
+    eng = nm.Engine(natoms=n, n_rep=ns, nt=nt, bulk_move=bool(bulk), skin=skin, skin_outer=oskin)
     eng.set_labels(et, pf, tt)
     t0 = time.time()
     eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(ns, .03125), dv=np.full(ns, .03125), dt=np.full(ns, .00390625))
@@ -45,7 +46,8 @@ def main():
         print("cycle %d: %.1f ms  atom-steps/s %.3e  sweeps/s %.3e  pair-flops %.2f TF/s  builds %d evals %d  listpairs/inpairs %.2f swaps %d  <ah> %.2f <av> %.2f <ap> %.2f" % (
             cyc, dt * 1e3, ct["hmc_atom_steps"] / dt, ct["sweeps"] / dt, flops / dt / 1e12, ct["list_builds"], ct["force_evals"],
             ct["list_pairs"] / max(1, ct["pairs_force"] + ct["pairs_full"]), sw, th[:, 17].mean(), th[:, 16].mean(), th[:, 15].mean()))
-        print("   clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
+        print("   per-call clk: outer %.0f inner %.0f vel %.0f | share outer %.2f inner %.2f vel %.2f" % (ct["clk_outer"] / max(1, ct["outer_builds"]), ct["clk_inner"] / max(1, ct["list_builds"]), ct["clk_vel"] / max(1, ct["hmc_moves"]), ct["clk_outer"] / ct["clk_total"], ct["clk_inner"] / ct["clk_total"], ct["clk_vel"] / ct["clk_total"]))
+        print("   outer builds %d | clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["outer_builds"], ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
     print("T col0 thermo:", np.round(th[:nt, :6], 3)[::max(1, nt // 4)])
 
 main()
