@@ -122,10 +122,12 @@ class Engine:
         self.mod, self.nstps = int(mod), int(nstps)
         cfg = NmConfig(C.sizeof(NmConfig), device, natoms, n_rep, self.n_rep_global, rep_offset, nt, precision,
                        nstps, mod, int(bool(bulk_move)), int(bool(text_rounding)), ppos, pvol, lat_scale, mass, rc,
-                       skin, skin_outer, seed, stream)
+                       skin, skin_outer, seed, None)
         self._h = C.c_void_p()
         _check(L.nm_create(C.byref(cfg), C.byref(self._h)))
         self._L = L
+        if stream is not None:      # 0 = the legacy default stream (what torch.cuda.current_stream() is by default)
+            _check(L.nm_set_stream(self._h, C.c_void_p(stream)))
 
     # -- lifetime
     def close(self):

@@ -1,0 +1,90 @@
+"""CPU tests that pin the oracle's LJ restatement (parity unpinned by the reference: LAMMPS is absent) with
+self-derived anchors: analytic fcc shell sums, three independent implementations, finite-difference forces."""
+import numpy as np
+import pytest
+
+A0 = (4 / 1.122) ** (1 / 3)
+
+
+def _liquid(orc, sz, rho, sigma, seed):
+    rng = np.random.default_rng(seed)
+    box = sz * (4 / rho) ** (1 / 3)
+    x = orc.fcc_positions(sz, box) + rng.normal(0, sigma, (4 * sz ** 3, 3))
+    return orc.wrap(x.reshape(-1), box).reshape(-1, 3), box
+
+
+def test_fcc_anchors(orc):
+    """E/N, W/(3V) of the perfect fcc crystal at rho* = 1.122, rc = 2.5 (SURVEY section 4 anchors, re-derived from shells)"""
+    e, w, nn = orc.fcc_shell_sum(A0)
+    assert nn == 78
+    assert abs(e - (-8.034879297835)) < 1e-11
+    for sz in (4, 5):
+        box = sz * A0
+        pe, W, f, npairs = orc.lj_eval_n2(orc.fcc_positions(sz, box), box)
+        n = 4 * sz ** 3
+        assert npairs == 39 * n
+        assert abs(pe / n - e) < 1e-11 and abs(W / n - w) < 1e-10
+        assert abs(W / (3 * box ** 3) - 3.540508883950) < 1e-10
+        assert np.abs(f).max() < 1e-12
+
+
+@pytest.mark.parametrize("sz,rho,sigma", [(4, 1.1, 0.05), (5, 0.9, 0.2), (5, 0.5, 0.5), (7, 0.8, 0.3)])
+def test_three_implementations_agree(orc, sz, rho, sigma):
+    x, box = _liquid(orc, sz, rho, sigma, seed=sz)
+    a = orc.lj_eval_n2(x, box)
+    b = orc.lj_eval_list(x, box)
+    c = orc.lj_eval_numpy(x, box)
+    assert a[3] == b[3] == c[3]
+    scale = max(abs(a[0]), 1.0)
+    assert abs(a[0] - b[0]) < 1e-13 * scale and abs(a[0] - c[0]) < 1e-12 * scale
+    assert abs(a[1] - b[1]) < 1e-12 * max(abs(a[1]), scale) and abs(a[1] - c[1]) < 1e-11 * max(abs(a[1]), scale)
+    fs = np.abs(a[2]).max()
+    assert np.abs(a[2] - b[2]).max() < 1e-13 * fs and np.abs(a[2] - c[2]).max() < 1e-12 * fs
+
+
+def test_forces_are_minus_gradient(orc):
+    x, box = _liquid(orc, 4, 0.95, 0.1, seed=2)
+    pe, w, f, _ = orc.lj_eval_n2(x, box)
+    h = 1e-6
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        i, c = rng.integers(256), rng.integers(3)
+        xp, xm = x.copy(), x.copy()
+        xp[i, c] += h
+        xm[i, c] -= h
+        fd = -(orc.lj_eval_n2(xp, box)[0] - orc.lj_eval_n2(xm, box)[0]) / (2 * h)
+        assert abs(fd - f[i, c]) < 1e-5 * max(1.0, abs(f[i, c]))
+    # virial = -dE/dlnV * 3 for a homogeneous scaling (no pair crosses the cutoff for a tiny strain is not guaranteed -> loose)
+    assert np.abs(f.sum(0)).max() < 1e-10 * np.abs(f).max()
+
+
+def test_single_atom_delta_equals_total_difference(orc):
+    x, box = _liquid(orc, 4, 1.0, 0.08, seed=4)
+    rng = np.random.default_rng(1)
+    e0 = orc.lj_eval_n2(x, box)[0]
+    for _ in range(8):
+        k = int(rng.integers(256))
+        xn = x[k] + rng.uniform(-0.1, 0.1, 3)
+        xn -= np.floor(xn / box) * box
+        y = x.copy()
+        y[k] = xn
+        assert abs(orc.lj_delta_atom(x, k, xn, box) - (orc.lj_eval_n2(y, box)[0] - e0)) < 1e-10
+
+
+def test_cycle_invariants(orc):
+    """one oracle cycle: counters add up, KE after a rejected HMC equals (3N-3)/2 T minus the rotation part, box is '%f'-rounded"""
+    x, box = _liquid(orc, 4, 1.0, 0.03, seed=7)
+    box = orc.round6(box)
+    p = orc.make_params(mod=40, bulk_move=1, seed=3)
+    xx, vv = x.reshape(-1).copy(), np.zeros(768)
+    scal, counts = np.array([box, .03125, .03125, .00390625]), np.zeros(6)
+    th, ct, tr = orc.cycle(p, [1.0, 2.0, 1.0, 1.0], 0, 0, xx, vv, scal, counts, trace=True)
+    assert counts[0] + counts[2] + counts[4] == 40 == ct[orc.CT_SWEEPS]
+    assert ct[orc.CT_HMC_ATOM_STEPS] == 256 * 8 * counts[4]
+    assert abs(scal[0] * 1e6 - round(scal[0] * 1e6)) < 1e-6
+    assert th[4] == scal[0] and abs(th[5] - scal[0] ** 3) < 1e-9
+    assert 0 <= xx.min() and xx.max() < scal[0]
+    dof = 3 * 256 - 3
+    assert abs(th[0] - 2 * th[2] / dof) < 1e-12
+    # pe of the trace's last row equals the reported pe
+    assert tr[-1, 0] == th[1]
