@@ -180,6 +180,8 @@ int  nm_get_counters(nm_engine* h, uint64_t* out);
 int  nm_reset_counters(nm_engine* h);
 /* number of kernels this engine has launched since nm_create (bench.py: gpu_launches) */
 int64_t nm_launch_count(nm_engine* h);
+/* SM clocks each local slot's CTA spent in the last cycle kernel (load-balance diagnostics): out[n_rep] */
+int  nm_get_cta_clocks(nm_engine* h, uint64_t* out);
 
 /* ---- a-14: calculate_rdf (lammps_distr.py:123-135) over a batch of samples.
  *   pos   : HOST or DEVICE float32 [nsamples][natoms][3] (dev_ptrs selects which)

@@ -13,7 +13,8 @@ _ROOT = os.path.dirname(_HERE)
 LIB = os.path.join(_HERE, "libnm_b200.so")
 _STAMP = os.path.join(_HERE, ".libnm_b200.stamp")
 
-NVCC_FLAGS = [
+EXTRA = os.environ.get("NM_NVCC_EXTRA", "").split()
+NVCC_FLAGS = EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]

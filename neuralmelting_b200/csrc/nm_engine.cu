@@ -24,12 +24,14 @@ constexpr int NCMAX = 8;                 // cell grid is at most 8^3
 constexpr int RED_DOUBLES = 32 * 12 + 12;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
+constexpr int NSMALL = 768;              // largest N handled by the all-pairs hit-matrix build (72 KB of bits)
 constexpr int ST_BOX = 1, ST_NEIGH = 2;  // status bits
 
 // ------------------------------------------------------------------ device-side engine description
 struct Dev {
   int N, Npad, nrep, nrep_global, rep_offset, nt, maxq, maxqo, maxnbo;   // inner / outer list capacity in quads, outer scratch entries
   int nstps, mod, bulk, text_rounding;
+  int small;                               // 1: N <= NSMALL: single-level list built from an all-pairs hit matrix in shared memory
   double ppos, pvol, lat, mass, rc, skin, oskin;
   uint32_t seed_lo, seed_hi;
   // per configuration
@@ -49,6 +51,8 @@ struct Dev {
   double *cnt;                             // [nrep][6]  ntp nap ntv nav nth nah
   double *list_pairs;                      // [nrep] listed unordered pairs of the current list
   int *cfg_slot, *slot_cfg;                // local permutation
+  unsigned long long* cta_clk;             // [nrep] SM clocks the configuration's CTA spent in the last cycle
+  int* order;                              // [nrep] blockIdx -> configuration (cost-balanced placement)
   int *status;                             // [nrep]
   // per local slot
   double *label;                           // [nrep][4] et pf temp temp_vel
@@ -63,6 +67,7 @@ struct Ctx {
   double Lsave;                 // box the saved copy (gxs) refers to
   double* sp;                   // shared positions, AoS: atom j at sp[3j..3j+2] (one address register per gather)
   float4* sf;                   // shared float32 fractional positions (list build prefilter only)
+  uint32_t* hbits;              // shared (small mode): N x N hit bit matrix, row i = atoms within the list radius of i
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
   uint16_t *cell_atoms, *atom_cell;
@@ -79,12 +84,15 @@ struct Ctx {
   int status;
 };
 
-__host__ __device__ inline size_t smem_bytes(int Npad) {
+// rows are padded to an odd number of words: consecutive atoms (lanes) then hit different banks
+__host__ __device__ inline size_t hbits_words(int N) { const size_t w = (N + 31) / 32; return w * 32 * (w | 1); }
+__host__ __device__ inline size_t smem_bytes(int Npad, int N, int small) {
   size_t b = sizeof(double) * (3 * (size_t)Npad + RED_DOUBLES + BC_DOUBLES + SHT_DOUBLES);
   b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8 + 2);   // +2: keeps the float4 block 16-byte aligned
   b += sizeof(float4) * (size_t)Npad;
   b += sizeof(unsigned long long) * 2;
   b += sizeof(uint16_t) * 2 * (size_t)Npad;
+  if (small) b += sizeof(uint32_t) * hbits_words(N);
   return b;
 }
 
@@ -103,6 +111,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.sf = reinterpret_cast<float4*>(q); q += 4 * d.Npad;
   uint16_t* h = reinterpret_cast<uint16_t*>(q);
   cx.cell_atoms = h; cx.atom_cell = h + d.Npad;
+  cx.hbits = reinterpret_cast<uint32_t*>(h + 2 * d.Npad);
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
   cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off; cx.gx0 = d.x0 + off;
@@ -164,6 +173,292 @@ __device__ void store_positions(Ctx& cx) {
   }
 }
 
+// force-loop quads carry their image code (0..26) in the 3 spare top bits of the first two indices (N <= 8191)
+__device__ __forceinline__ ushort4 pack_code(ushort4 v, int code) {
+  v.x = (unsigned short)(v.x | ((code & 7) << 13)); v.y = (unsigned short)(v.y | ((code >> 3) << 13));
+  return v;
+}
+
+// ------------------------------------------------------------------ list construction helpers
+// Per-atom list rows grouped by periodic image. A pair enters when its float32 distance is below the list radius
+// times (1+margin); the margin covers the float32 rounding of the fractional coordinates (<= 2^-24 each, < 4e-6
+// relative on r^2), so the row is a superset of the exact list. With box >= 2 r_list the image of a neighbour along
+// one axis is either 0 or one fixed sign per atom (-1 for atoms in the lower half of the box, +1 in the upper
+// half): at most 8 image groups, g = (kx != 0) | (ky != 0) << 1 | (kz != 0) << 2, counted in packed registers.
+// Pass A streams the hits (discovery order) into the owner's scratch row with 16-byte stores; pass B sweeps that row
+// once per non-empty group and emits whole quads (8 bytes).
+// Candidates: all atoms (nc == 1), the 27 stencil cells (nc >= 3), or -- BITS -- the set bits of the atom's row in the
+// shared-memory hit matrix. Output: OUTER rows (row-major per atom) or, BITS mode, the [quad][atom] force-loop layout.
+template <bool BITS>
+__device__ int grouped_rows(const Dev& d, Ctx& cx, float rl2f, int nc) {
+  const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
+  const double invL = 1.0 / cx.L;
+  const float magic = 12582912.f;          // 1.5 * 2^23: (x + magic) - magic = rint(x) for |x| < 2^22
+  const bool grouped = !cx.mic;
+  const int trow_len = (d.maxnbo + 3) & ~3, capq = BITS ? d.maxq : d.maxqo;
+  const int W = (N + 31) / 32;
+  int over = 0;
+  double tot = 0.0;
+  for (int i = tid; i < N; i += nthr) {
+    const float4 pi = cx.sf[i];
+    uint32_t* trow = cx.ltmp + (size_t)i * trow_len;
+    unsigned long long gcnt_lo = 0ull, gcnt_hi = 0ull;   // 8 image-group counters, 16 bits each
+    int cnt = 0;
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    auto test = [&](int j) {
+      const float4 pj = cx.sf[j];
+      float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      const float kx = __fadd_rn(__fadd_rn(dx, magic), -magic), ky = __fadd_rn(__fadd_rn(dy, magic), -magic),
+                  kz = __fadd_rn(__fadd_rn(dz, magic), -magic);
+      dx -= kx; dy -= ky; dz -= kz;
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      if (BITS || (r2 < rl2f && j != i)) {
+        if (cnt < d.maxnbo) {
+          const int g = grouped ? ((kx != 0.f) | ((ky != 0.f) << 1) | ((kz != 0.f) << 2)) : 0;
+          const uint32_t en = (uint32_t)j | ((uint32_t)g << 16);
+          const int slot = cnt & 3;
+          if (!BITS) {
+            b0 = slot == 0 ? en : b0; b1 = slot == 1 ? en : b1; b2 = slot == 2 ? en : b2; b3 = slot == 3 ? en : b3;
+            if (slot == 3) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
+          }
+          if (g < 4) gcnt_lo += 1ull << (16 * g); else gcnt_hi += 1ull << (16 * (g - 4));
+        }
+        cnt++;
+      }
+    };
+    if (BITS) {
+      const uint32_t* row = cx.hbits + (size_t)i * (W | 1);
+      for (int w = 0; w < W; w++) {
+        uint32_t m = row[w];
+        while (m) { const int b = __ffs(m) - 1; m &= m - 1; test(w * 32 + b); }
+      }
+    } else if (nc == 1) {
+      for (int j = 0; j < N; j++) test(j);
+    } else {
+      const int ci = cx.atom_cell[i], a = ci / (nc * nc), b = (ci / nc) % nc, e = ci % nc;
+      for (int da = -1; da <= 1; da++) for (int db = -1; db <= 1; db++) for (int de = -1; de <= 1; de++) {
+        const int cc = (((a + da + nc) % nc) * nc + (b + db + nc) % nc) * nc + (e + de + nc) % nc;
+        const int s = cx.cell_start[cc], en = cx.cell_start[cc + 1];
+        for (int p = s; p < en; p++) test(cx.cell_atoms[p]);
+      }
+    }
+    if (cnt > d.maxnbo) { over = 1; cnt = d.maxnbo; }
+    if (!BITS && (cnt & 3)) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
+    ushort4* orow = cx.olist + (size_t)i * d.maxqo;
+    uint8_t* crow = cx.ocode + (size_t)i * d.maxqo;
+    const int sx = pi.x < 0.5f ? -1 : 1, sy = pi.y < 0.5f ? -1 : 1, sz = pi.z < 0.5f ? -1 : 1;
+    int q = 0;
+    auto emit = [&](ushort4 v, int code) {
+      if (BITS) cx.list[(size_t)q * Npad + i] = pack_code(v, code);
+      else { orow[q] = v; crow[q] = (uint8_t)code; }
+      q++;
+    };
+    for (int g = 0; g < 8; g++) {
+      const int ng = (int)(((g < 4 ? gcnt_lo >> (16 * g) : gcnt_hi >> (16 * (g - 4)))) & 0xffffull);
+      if (ng == 0) continue;
+      if (q + ((ng + 3) >> 2) > capq) { over = 1; break; }
+      const int code = 13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz;
+      unsigned short a0 = (unsigned short)N, a1 = a0, a2 = a0, a3 = a0;
+      int fill = 0;
+      auto take = [&](unsigned short j) {
+        a0 = fill == 0 ? j : a0; a1 = fill == 1 ? j : a1; a2 = fill == 2 ? j : a2; a3 = fill == 3 ? j : a3;
+        if (++fill == 4) { emit(make_ushort4(a0, a1, a2, a3), code); fill = 0; a0 = a1 = a2 = a3 = (unsigned short)N; }
+      };
+      if (BITS) {
+        // re-walk the atom's bit row (shared memory) and recompute the image group of each hit: no global scratch
+        const uint32_t* row = cx.hbits + (size_t)i * (W | 1);
+        for (int w = 0; w < W; w++) {
+          uint32_t m = row[w];
+          while (m) {
+            const int j = w * 32 + __ffs(m) - 1; m &= m - 1;
+            int gj = 0;
+            if (grouped) {
+              const float4 pj = cx.sf[j];
+              const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+              gj = (__fadd_rn(__fadd_rn(dx, magic), -magic) != 0.f) | ((__fadd_rn(__fadd_rn(dy, magic), -magic) != 0.f) << 1) |
+                   ((__fadd_rn(__fadd_rn(dz, magic), -magic) != 0.f) << 2);
+            }
+            if (gj == g) take((unsigned short)j);
+          }
+        }
+      } else {
+        uint4 e4 = *reinterpret_cast<const uint4*>(trow);
+        for (int t = 0; t < cnt; t += 4) {
+          const uint4 n4 = (t + 4 < cnt) ? *reinterpret_cast<const uint4*>(trow + t + 4) : e4;
+          const uint32_t ee[4] = { e4.x, e4.y, e4.z, e4.w };
+          e4 = n4;
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (t + u < cnt && (int)(ee[u] >> 16) == g) take((unsigned short)(ee[u] & 0xffffu));
+        }
+      }
+      if (fill) emit(make_ushort4(a0, a1, a2, a3), code);
+    }
+    if (BITS) {
+      cx.nnb[i] = (uint16_t)q;
+      cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+      tot += cnt;
+    } else {
+      cx.onq[i] = (uint16_t)q;
+      cx.gx0o[i] = cx.sp[3 * i] * invL; cx.gx0o[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0o[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+    }
+  }
+  if (BITS) {
+    double r[1] = { tot };
+    block_sum<1>(r, cx.red);
+    cx.list_pairs = 0.5 * r[0];
+  }
+  return over;
+}
+
+// SMALL mode extraction: the owner walks its bit row twice. Pass 1 counts the hits per image group (8 packed 16-bit
+// counters), pass 2 stores every index straight into its final slot of the [quad][atom] layout using packed per-group
+// cursors -- two passes whatever the number of groups, no scratch memory. Image codes ride in the top 3 bits of the
+// first two indices of each quad; groups are padded to whole quads with the dummy atom N.
+__device__ int extract_rows_small(const Dev& d, Ctx& cx) {
+  const int N = cx.N, Npad = cx.Npad, W = (N + 31) / 32, WS = W | 1;
+  const double invL = 1.0 / cx.L;
+  const bool grouped = !cx.mic;
+  uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
+  int over = 0; double tot = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 pi = cx.sf[i];
+    const uint32_t* row = cx.hbits + (size_t)i * WS;
+    // image group of a listed neighbour: along an axis the fractional difference of a pair within the list radius
+    // is either below r_list/L < 1/2 in magnitude (same image) or above 1 - r_list/L > 1/2 (adjacent image)
+    auto group_of = [&](int j) -> int {
+      if (!grouped) return 0;
+      const float4 pj = cx.sf[j];
+      return (fabsf(pi.x - pj.x) > 0.5f) | ((fabsf(pi.y - pj.y) > 0.5f) << 1) | ((fabsf(pi.z - pj.z) > 0.5f) << 2);
+    };
+    unsigned long long c_lo = 0ull, c_hi = 0ull;
+    int cnt = 0;
+    // flattened walk over the set bits: every lane advances through ITS hits, so a warp iterates max(hits) times
+    // instead of sum over words of max(popcount)
+    {
+      int w = 0; uint32_t m = row[0];
+      for (;;) {
+        while (m == 0u && ++w < W) m = row[w];
+        if (w >= W) break;
+        const int j = w * 32 + __ffs(m) - 1; m &= m - 1;
+        const int g = group_of(j);
+        if (g < 4) c_lo += 1ull << (16 * g); else c_hi += 1ull << (16 * (g - 4));
+        cnt++;
+      }
+    }
+    // exclusive prefix of the quad-padded group sizes -> start slot (in entries) of every group
+    unsigned long long s_lo = 0ull, s_hi = 0ull;
+    int run = 0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+      const int ng = (int)(((g < 4 ? c_lo >> (16 * g) : c_hi >> (16 * (g - 4)))) & 0xffffull);
+      if (g < 4) s_lo |= (unsigned long long)run << (16 * g); else s_hi |= (unsigned long long)run << (16 * (g - 4));
+      run += (ng + 3) & ~3;
+    }
+    const int nq = run >> 2;
+    if (nq > d.maxq) { over = 1; cx.nnb[i] = 0; continue; }
+    const int sx = pi.x < 0.5f ? -1 : 1, sy = pi.y < 0.5f ? -1 : 1, sz = pi.z < 0.5f ? -1 : 1;
+    unsigned long long codes = 0ull;                       // the 8 group codes, 5 bits each
+#pragma unroll
+    for (int g = 0; g < 8; g++) codes |= (unsigned long long)(13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz) << (5 * g);
+    auto put = [&](int pos, int j, int g) {
+      const int code = (int)(codes >> (5 * g)) & 31;
+      const int slot = pos & 3;
+      const int v = j | (slot == 0 ? (code & 7) << 13 : (slot == 1 ? (code >> 3) << 13 : 0));
+      l16[((size_t)(pos >> 2) * Npad + i) * 4 + slot] = (uint16_t)v;
+    };
+    unsigned long long f_lo = s_lo, f_hi = s_hi;           // running cursors
+    {
+      int w = 0; uint32_t m = row[0];
+      for (;;) {
+        while (m == 0u && ++w < W) m = row[w];
+        if (w >= W) break;
+        const int j = w * 32 + __ffs(m) - 1; m &= m - 1;
+        const int g = group_of(j);
+        const int pos = (int)(((g < 4 ? f_lo >> (16 * g) : f_hi >> (16 * (g - 4)))) & 0xffffull);
+        if (g < 4) f_lo += 1ull << (16 * g); else f_hi += 1ull << (16 * (g - 4));
+        put(pos, j, g);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++) {                           // pad every group to a whole quad with the dummy atom
+      int pos = (int)(((g < 4 ? f_lo >> (16 * g) : f_hi >> (16 * (g - 4)))) & 0xffffull);
+      const int ng = (int)(((g < 4 ? c_lo >> (16 * g) : c_hi >> (16 * (g - 4)))) & 0xffffull);
+      if (ng) for (; pos & 3; pos++) put(pos, N, g);
+    }
+    cx.nnb[i] = (uint16_t)nq;
+    cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+    tot += cnt;
+  }
+  double r[1] = { tot };
+  block_sum<1>(r, cx.red);
+  cx.list_pairs = 0.5 * r[0];
+  return over;
+}
+
+// re-wrap every atom into [0,L) (shifting the revert copy by the same lattice vector) and refresh the float32
+// fractional copies; entries N..Npad-1 are parked far away so that padded indices never test positive
+__device__ void wrap_and_refresh(Ctx& cx, bool wrap) {
+  const int N = cx.N, Npad = cx.Npad;
+  const double L = cx.L, invL = 1.0 / L;
+  for (int i = threadIdx.x; i < Npad; i += blockDim.x) {
+    if (i < N) {
+      if (wrap) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          const double x = cx.sp[3 * i + a], xw = wrap1(x - floor(x * invL) * L, L);
+          if (xw != x) { cx.sp[3 * i + a] = xw; cx.gxs[a * Npad + i] += (xw - x) * (cx.Lsave * invL); }
+        }
+      }
+      cx.sf[i] = make_float4((float)(cx.sp[3 * i] * invL), (float)(cx.sp[3 * i + 1] * invL), (float)(cx.sp[3 * i + 2] * invL), 0.f);
+    } else cx.sf[i] = make_float4(1e6f, 1e6f, 1e6f, 0.f);
+  }
+}
+
+// SMALL mode (N <= NSMALL): every unordered pair is tested ONCE, 32 x 32 tile by tile, on the FP32 pipe; the warp
+// ballot of each column gives the transposed bits, so both rows of the symmetric hit matrix are written without
+// atomics. The list is then single level (radius rc + skin) and is rebuilt from scratch each time.
+__device__ void build_small(const Dev& d, Ctx& cx) {
+  const int N = cx.N, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
+  const int W = (N + 31) / 32;
+  cx.mic = L < 2.0 * rl * (1.0 + 1e-3);
+  __syncthreads();
+  wrap_and_refresh(cx, true);
+  __syncthreads();
+  const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
+  const float magic = 12582912.f;
+  const int ntile = W * (W + 1) / 2;
+  const long long t_tiles0 = clock64();
+  for (int t = wid; t < ntile; t += nw) {
+    int ti = 0, rem = t;                      // tile (ti, tj), ti <= tj, enumerated row by row
+    while (rem >= W - ti) { rem -= W - ti; ti++; }
+    const int tj = ti + rem;
+    const int i = ti * 32 + lane;
+    const float4 pi = cx.sf[i < cx.Npad ? i : cx.Npad - 1];
+    uint32_t mask = 0, colmask = 0;
+    for (int jj = 0; jj < 32; jj++) {
+      const int j = tj * 32 + jj;
+      const float4 pj = cx.sf[j < cx.Npad ? j : cx.Npad - 1];
+      float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      dx -= __fadd_rn(__fadd_rn(dx, magic), -magic); dy -= __fadd_rn(__fadd_rn(dy, magic), -magic); dz -= __fadd_rn(__fadd_rn(dz, magic), -magic);
+      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      const bool hit = r2 < rl2f && i != j && i < N && j < N;
+      const uint32_t col = __ballot_sync(0xffffffffu, hit);
+      mask |= hit ? (1u << jj) : 0u;
+      colmask = lane == jj ? col : colmask;
+    }
+    cx.hbits[(size_t)i * (W | 1) + tj] = mask;
+    if (ti != tj) cx.hbits[(size_t)(tj * 32 + lane) * (W | 1) + ti] = colmask;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t_tiles0);
+  const int over = extract_rows_small(d, cx);
+  if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
+  cx.L0 = L; cx.L0o = L;
+  update_thr(d, cx);
+}
+
 // ------------------------------------------------------------------ two-level Verlet lists (deterministic)
 // OUTER list (radius rlo = rc + skin + oskin): cell-binned search on the FP32 pipe, rebuilt rarely. Per atom i it
 // holds neighbour quads GROUPED BY PERIODIC IMAGE: every quad carries one image code (kx+1)*9+(ky+1)*3+(kz+1),
@@ -182,14 +477,7 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
   const int ncell = nc * nc * nc;
   cx.mic = L < 2.0 * rlo * (1.0 + 1e-3);    // small box: the nearest image of a listed pair may change between builds
   __syncthreads();
-  for (int i = tid; i < N; i += nthr) {
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      const double x = cx.sp[3 * i + a], xw = wrap1(x - floor(x * invL) * L, L);
-      if (xw != x) { cx.sp[3 * i + a] = xw; cx.gxs[a * Npad + i] += (xw - x) * (cx.Lsave * invL); }
-    }
-    cx.sf[i] = make_float4((float)(cx.sp[3 * i] * invL), (float)(cx.sp[3 * i + 1] * invL), (float)(cx.sp[3 * i + 2] * invL), 0.f);
-  }
+  wrap_and_refresh(cx, true);
   __syncthreads();
   if (nc > 1) {
     for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
@@ -231,86 +519,8 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
     }
     __syncthreads();
   }
-  // a pair enters the list when its float32 distance is below rlo*(1+margin); the margin covers the float32 rounding
-  // of the fractional coordinates (<= 2^-24 each, < 4e-6 relative on r^2), so the list is a superset of {r < rlo}.
-  // Build-side arrays (scratch, outer list, outer codes) are ROW-MAJOR PER ATOM so that the owning thread streams
-  // them with 16-byte accesses. With box >= 2 rlo the image of a neighbour along one axis is either 0 or one fixed
-  // sign per atom (-1 for atoms in the lower half of the box, +1 in the upper half): at most 8 image groups,
-  // indexed g = (kx != 0) | (ky != 0) << 1 | (kz != 0) << 2, counted in one packed 64-bit register.
   const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
-  const float magic = 12582912.f;          // 1.5 * 2^23: (x + magic) - magic = rint(x) for |x| < 2^22
-  const bool grouped = !cx.mic;
-  const int trow_len = (d.maxnbo + 3) & ~3;
-  int over = 0;
-  for (int i = tid; i < N; i += nthr) {
-    const float4 pi = cx.sf[i];
-    uint32_t* trow = cx.ltmp + (size_t)i * trow_len;
-    unsigned long long gcnt_lo = 0ull, gcnt_hi = 0ull;   // 8 image-group counters, 16 bits each
-    int cnt = 0;
-    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    auto test = [&](int j) {                 // pass A: hits in discovery order -> scratch row, count per image group
-      const float4 pj = cx.sf[j];
-      float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      const float kx = __fadd_rn(__fadd_rn(dx, magic), -magic), ky = __fadd_rn(__fadd_rn(dy, magic), -magic),
-                  kz = __fadd_rn(__fadd_rn(dz, magic), -magic);
-      dx -= kx; dy -= ky; dz -= kz;
-      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      if (r2 < rl2f && j != i) {
-        if (cnt < d.maxnbo) {
-          const int g = grouped ? ((kx != 0.f) | ((ky != 0.f) << 1) | ((kz != 0.f) << 2)) : 0;
-          const uint32_t en = (uint32_t)j | ((uint32_t)g << 16);
-          const int slot = cnt & 3;
-          b0 = slot == 0 ? en : b0; b1 = slot == 1 ? en : b1; b2 = slot == 2 ? en : b2; b3 = slot == 3 ? en : b3;
-          if (slot == 3) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
-          if (g < 4) gcnt_lo += 1ull << (16 * g); else gcnt_hi += 1ull << (16 * (g - 4));
-        }
-        cnt++;
-      }
-    };
-    if (nc == 1) {
-      for (int j = 0; j < N; j++) test(j);
-    } else {
-      const int ci = cx.atom_cell[i], a = ci / (nc * nc), b = (ci / nc) % nc, e = ci % nc;
-      for (int da = -1; da <= 1; da++) for (int db = -1; db <= 1; db++) for (int de = -1; de <= 1; de++) {
-        const int cc = (((a + da + nc) % nc) * nc + (b + db + nc) % nc) * nc + (e + de + nc) % nc;
-        const int s = cx.cell_start[cc], en = cx.cell_start[cc + 1];
-        for (int p = s; p < en; p++) test(cx.cell_atoms[p]);
-      }
-    }
-    if (cnt > d.maxnbo) { over = 1; cnt = d.maxnbo; }
-    if (cnt & 3) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
-    // pass B: one sweep of the scratch row per non-empty image group; quads are written whole (8 bytes)
-    ushort4* orow = cx.olist + (size_t)i * d.maxqo;
-    uint8_t* crow = cx.ocode + (size_t)i * d.maxqo;
-    const int sx = pi.x < 0.5f ? -1 : 1, sy = pi.y < 0.5f ? -1 : 1, sz = pi.z < 0.5f ? -1 : 1;
-    int q = 0;
-    for (int g = 0; g < 8; g++) {
-      const int ng = (int)(((g < 4 ? gcnt_lo >> (16 * g) : gcnt_hi >> (16 * (g - 4)))) & 0xffffull);
-      if (ng == 0) continue;
-      if (q + ((ng + 3) >> 2) > d.maxqo) { over = 1; break; }
-      const int code = 13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz;
-      unsigned short a0 = (unsigned short)N, a1 = a0, a2 = a0, a3 = a0;
-      int fill = 0;
-      for (int t = 0; t < cnt; t += 4) {
-        const uint4 e4 = *reinterpret_cast<const uint4*>(trow + t);
-        const uint32_t ee[4] = { e4.x, e4.y, e4.z, e4.w };
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (t + u < cnt && (int)(ee[u] >> 16) == g) {
-            const unsigned short j = (unsigned short)(ee[u] & 0xffffu);
-            a0 = fill == 0 ? j : a0; a1 = fill == 1 ? j : a1; a2 = fill == 2 ? j : a2; a3 = fill == 3 ? j : a3;
-            if (++fill == 4) {
-              orow[q] = make_ushort4(a0, a1, a2, a3); crow[q] = (uint8_t)code; q++;
-              fill = 0; a0 = a1 = a2 = a3 = (unsigned short)N;
-            }
-          }
-        }
-      }
-      if (fill) { orow[q] = make_ushort4(a0, a1, a2, a3); crow[q] = (uint8_t)code; q++; }
-    }
-    cx.onq[i] = (uint16_t)q;
-    cx.gx0o[i] = cx.sp[3 * i] * invL; cx.gx0o[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0o[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
-  }
+  const int over = grouped_rows<false>(d, cx, rl2f, nc);
   if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
   cx.L0o = L;
   update_thr(d, cx);
@@ -323,9 +533,7 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
   __syncthreads();
-  for (int i = tid; i < Npad; i += nthr)
-    cx.sf[i] = i < N ? make_float4((float)(cx.sp[3 * i] * invL), (float)(cx.sp[3 * i + 1] * invL), (float)(cx.sp[3 * i + 2] * invL), 0.f)
-                     : make_float4(1e6f, 1e6f, 1e6f, 0.f);
+  wrap_and_refresh(cx, false);
   __syncthreads();
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
   const float magic = 12582912.f;
@@ -339,7 +547,7 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
     unsigned short a0 = (unsigned short)N, a1 = a0, a2 = a0, a3 = a0;
     int oq = 0, fill = 0, curcode = 13, cnt = 0;
     auto flush = [&]() {
-      if (oq < d.maxq) { cx.list[(size_t)oq * Npad + i] = make_ushort4(a0, a1, a2, a3); cx.qcode[(size_t)oq * Npad + i] = (uint8_t)curcode; }
+      if (oq < d.maxq) cx.list[(size_t)oq * Npad + i] = pack_code(make_ushort4(a0, a1, a2, a3), curcode);
       else over = 1;
       oq++; fill = 0; a0 = a1 = a2 = a3 = (unsigned short)N;
     };
@@ -383,6 +591,11 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
 // (re)build: make sure the outer list can still supply every pair within rl, then regenerate the inner list
 __device__ void build_list(const Dev& d, Ctx& cx) {
   const long long t_build0 = clock64();
+  if (d.small) {
+    build_small(d, cx);
+    if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; const unsigned long long dt = (unsigned long long)(clock64() - t_build0); cx.ct[NM_CT_CLK_BUILD] += dt; cx.ct[NM_CT_CLK_INNER] += dt; }
+    return;
+  }
   int flag = cx.thro2 < 0.0;
   if (!flag) {
     const double invL = 1.0 / cx.L;
@@ -430,13 +643,21 @@ __device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs
   if (MIC) { dx = mic_fast(dx, L_hi, L_lo, hL_hi); dy = mic_fast(dy, L_hi, L_lo, hL_hi); dz = mic_fast(dz, L_hi, L_lo, hL_hi); }
   const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
   const bool in = __double_as_longlong(rsq) < rc2_bits;
+#ifndef NM_RCP_EXACT      // default: FP32-seeded reciprocal; -DNM_RCP_EXACT selects the < 1 ulp variant
+  float yf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)rsq));   // 22-bit seed from the FP32 special-function unit
+  double y = (double)yf;
+  double t = fma(-rsq, y, 1.0);
+  const double r2inv = fma(y, t, y);                    // one Newton step: relative error < 6e-14
+#else
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
-  double t = fma(-rsq, y, 1.0);                         // seed is good to ~2^-9: cubic step, then a quadratic one
+  double t = fma(-rsq, y, 1.0);                         // seed is good to 2^-19.9 (measured): cubic step, then a quadratic one
   t = fma(t, t, t);
   y = fma(y, t, y);
   t = fma(-rsq, y, 1.0);
   const double r2inv = fma(y, t, y);                    // relative error ~ seed^6 (< 1 ulp)
+#endif
   const double r6inv = r2inv * r2inv * r2inv;
   double fpair = r6inv * fma(48.0, r6inv, -24.0) * r2inv;
   // outside the cutoff the high word is zeroed: the operand becomes a denormal (< 1e-308) whose products vanish
@@ -466,19 +687,21 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const int nq = cx.nnb[i];
     const ushort4* lp = cx.list + i;
-    const uint8_t* cp = cx.qcode + i;
     ushort4 cur = nq > 0 ? lp[0] : make_ushort4(0, 0, 0, 0);
-    int code = (!MIC && nq > 0) ? cp[0] : 13;
     for (int q = 0; q < nq; q++) {
+      // the quad two iterations ahead is pulled into L1 (no register cost); the next one is loaded here
+      if (q + 2 < nq) asm volatile("prefetch.global.L1 [%0];" :: "l"(lp + (size_t)(q + 2) * Npad));
       const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
-      const int ncode = (!MIC && q + 1 < nq) ? cp[(size_t)(q + 1) * Npad] : 13;
       double xs = xi, ys = yi, zs = zi;
-      if (!MIC) { xs -= cx.sht[3 * code]; ys -= cx.sht[3 * code + 1]; zs -= cx.sht[3 * code + 2]; }
-      lj_pair<EW, MIC>(cx.sp + 3 * cur.x, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(cx.sp + 3 * cur.y, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      if (!MIC) {
+        const int code = (cur.x >> 13) | ((cur.y >> 13) << 3);
+        xs -= cx.sht[3 * code]; ys -= cx.sht[3 * code + 1]; zs -= cx.sht[3 * code + 2];
+      }
+      lj_pair<EW, MIC>(cx.sp + 3 * (cur.x & 0x1fff), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * (cur.y & 0x1fff), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       lj_pair<EW, MIC>(cx.sp + 3 * cur.z, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       lj_pair<EW, MIC>(cx.sp + 3 * cur.w, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      cur = nxt; code = ncode;
+      cur = nxt;
     }
     cx.gf[i] = fx; cx.gf[Npad + i] = fy; cx.gf[2 * Npad + i] = fz;
     if (KICK) {
@@ -784,7 +1007,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
           const int nq = cx.nnb[kk];
           for (int q = lane; q < nq; q += 32) {
             const ushort4 e4 = cx.list[(size_t)q * Npad + kk];
-            pair(e4.x); pair(e4.y); pair(e4.z); pair(e4.w);
+            pair(e4.x & 0x1fff); pair(e4.y & 0x1fff); pair(e4.z); pair(e4.w);
           }
         }
         for (int o = 16; o > 0; o >>= 1) { de += __shfl_xor_sync(0xffffffffu, de, o); vis += __shfl_xor_sync(0xffffffffu, vis, o); }
@@ -859,7 +1082,7 @@ template <int NTHR>
 __global__ void __launch_bounds__(NTHR, 1024 / NTHR)
 k_cycle(Dev d, long long cycle) {
   extern __shared__ __align__(16) unsigned char smem[];
-  Ctx cx; ctx_init(d, cx, blockIdx.x, smem);
+  Ctx cx; ctx_init(d, cx, d.order[blockIdx.x], smem);
   const int c = cx.c, slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
   const long long t_cycle0 = clock64();
   const double et = d.label[4 * slot], pf = d.label[4 * slot + 1], t_vel = d.label[4 * slot + 3];
@@ -902,8 +1125,39 @@ k_cycle(Dev d, long long cycle) {
     d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.L0o[c] = cx.L0o; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs;
     if (cx.status) d.status[c] |= cx.status;
     cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
-    cx.ct[NM_CT_CLK_TOTAL] += (unsigned long long)(clock64() - t_cycle0);
+    const unsigned long long dt_cycle = (unsigned long long)(clock64() - t_cycle0);
+    cx.ct[NM_CT_CLK_TOTAL] += dt_cycle;
+    d.cta_clk[c] = dt_cycle;
     for (int k = 0; k < NM_COUNTER_WIDTH; k++) if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]);
+  }
+}
+
+// Cost-balanced CTA placement for the next cycle. Blocks b and b + nsm share an SM when two CTAs fit per SM and
+// nrep <= 2 nsm (the block scheduler fills SMs round-robin). With last cycle's per-configuration clocks sorted in
+// descending order, the nsm-(nrep-nsm) SMs that hold a single CTA get the most expensive configurations and every
+// other SM pairs an expensive with a cheap one. Larger grids are launched in descending cost (longest first).
+__global__ void k_schedule(Dev d, int nsm, int per_sm) {
+  extern __shared__ unsigned long long sclk[];
+  int* sorted = reinterpret_cast<int*>(sclk + d.nrep);
+  for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) sclk[c] = d.cta_clk[c];
+  __syncthreads();
+  for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) {
+    const unsigned long long v = sclk[c];
+    int rank = 0;
+    for (int o = 0; o < d.nrep; o++) rank += (sclk[o] > v) || (sclk[o] == v && o < c);
+    sorted[rank] = c;
+  }
+  __syncthreads();
+  const int n = d.nrep;
+  for (int b = threadIdx.x; b < n; b += blockDim.x) {
+    int pick = b;
+    if (per_sm == 2 && n > nsm && n <= 2 * nsm) {
+      const int npair = n - nsm, nsingle = nsm - npair;
+      if (b < npair) pick = nsingle + b;                 // first CTA of a shared SM: next most expensive
+      else if (b < nsm) pick = b - npair;                // SM with a single CTA: the most expensive ones
+      else pick = n - 1 - (b - nsm);                     // second CTA of shared SM (b - nsm): the cheapest
+    }
+    d.order[b] = sorted[pick];
   }
 }
 
@@ -1028,7 +1282,7 @@ struct nm_engine {
   nm_config cfg;
   Dev d;
   cudaStream_t stream; bool own_stream;
-  int threads; size_t smem;
+  int threads; size_t smem; int nsm;
   std::vector<void*> allocs;
   double *stage_a, *stage_b, *stage_s;     // device staging: x/v AoS [nrep][3N], scalars [nrep][8]
   double *ex_table, *ex_et, *ex_pf, *ex_uni, *ex_scratch; int *ex_perm, *ex_tmp; unsigned long long* ex_swaps;
@@ -1062,7 +1316,7 @@ int nm_device_count(void) {
 int nm_create(const nm_config* cfg, nm_engine** out) {
   if (!cfg || !out) return fail(NM_EINVAL, "nm_create: null argument");
   if (cfg->struct_size != (int32_t)sizeof(nm_config)) return fail(NM_EINVAL, "nm_create: nm_config size mismatch (%d vs %zu)", cfg->struct_size, sizeof(nm_config));
-  if (cfg->natoms < 2 || cfg->natoms > 65000) return fail(NM_EINVAL, "nm_create: natoms %d out of range [2, 65000]", cfg->natoms);
+  if (cfg->natoms < 2 || cfg->natoms > 8000) return fail(NM_EINVAL, "nm_create: natoms %d out of range [2, 8000] (13-bit neighbour indices; shared memory holds ~5000 atoms)", cfg->natoms);
   if (cfg->n_rep < 1 || cfg->nt < 1 || cfg->n_rep % cfg->nt || cfg->rep_offset % cfg->nt || cfg->n_rep_global < cfg->rep_offset + cfg->n_rep)
     return fail(NM_EINVAL, "nm_create: local slots must be whole pressure rows (n_rep=%d rep_offset=%d nt=%d global=%d)", cfg->n_rep, cfg->rep_offset, cfg->nt, cfg->n_rep_global);
   if (cfg->precision != 64 && cfg->precision != 0) return fail(NM_EINVAL, "nm_create: precision %d not available in this build (64 only)", cfg->precision);
@@ -1102,7 +1356,9 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     d.maxqo = ((maxnbo + 3) / 4 + 8 + 1) & ~1;
   }
   h->threads = N <= 256 ? 256 : (N <= 512 ? 512 : 1024);   // 64 registers/thread: 32 warps per SM hide the FP64 latency
-  h->smem = smem_bytes(d.Npad);
+  d.small = N <= NSMALL;
+  h->smem = smem_bytes(d.Npad, N, d.small);
+  { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, cfg->device) == cudaSuccess) h->nsm = pr.multiProcessorCount; else h->nsm = 148; }
   if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
   const size_t per = (size_t)nrep * 3 * d.Npad;
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, per);
@@ -1112,7 +1368,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
-  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep);
+  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.order, nrep);
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
@@ -1123,6 +1379,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     std::vector<double> neg(nrep, -1.0);
     cudaError_t e1 = cudaMemcpy(d.cfg_slot, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
     cudaError_t e2 = cudaMemcpy(d.slot_cfg, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(d.order, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
     cudaError_t e3 = cudaMemcpy(d.L0, neg.data(), sizeof(double) * nrep, cudaMemcpyHostToDevice);
     if (e3 == cudaSuccess) e3 = cudaMemcpy(d.L0o, neg.data(), sizeof(double) * nrep, cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "nm_create: init copy failed"); }
@@ -1257,6 +1514,12 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   else k_cycle<1024><<<h->d.nrep, 1024, h->smem, h->stream>>>(h->d, (long long)cycle);
   h->launches++;
   CK(cudaGetLastError());
+  if (h->d.nrep > h->nsm && h->d.nrep <= 4096) {        // placement for the next cycle from this cycle's clocks
+    const int per_sm = (h->smem * 2 <= 220 * 1024 && h->threads <= 512) ? 2 : 1;
+    k_schedule<<<1, 1024, h->d.nrep * (sizeof(unsigned long long) + sizeof(int)), h->stream>>>(h->d, h->nsm, per_sm);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
   h->have_thermo = true;
   return NM_OK;
 }
@@ -1341,5 +1604,16 @@ int nm_reset_counters(nm_engine* h) {
   return NM_OK;
 }
 int64_t nm_launch_count(nm_engine* h) { return h ? h->launches : 0; }
+
+int nm_get_cta_clocks(nm_engine* h, uint64_t* out) {
+  if (!h || !out) return fail(NM_EINVAL, "nm_get_cta_clocks: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<unsigned long long> clk(h->d.nrep); std::vector<int> cs(h->d.nrep);
+  CK(cudaMemcpyAsync(clk.data(), h->d.cta_clk, sizeof(unsigned long long) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(cs.data(), h->d.cfg_slot, sizeof(int) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < h->d.nrep; c++) out[cs[c]] = clk[c];
+  return NM_OK;
+}
 
 }  // extern "C"

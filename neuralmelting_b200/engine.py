@@ -61,6 +61,7 @@ def load_library():
     for name in ("nm_destroy", "nm_synchronize", "nm_adapt", "nm_reset_counters"):
         getattr(L, name).argtypes = [C.c_void_p]
     L.nm_launch_count.argtypes = [C.c_void_p]
+    L.nm_get_cta_clocks.argtypes = [C.c_void_p, C.c_void_p]
     L.nm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.nm_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.nm_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
@@ -228,6 +229,11 @@ class Engine:
 
     def launch_count(self):
         return int(self._L.nm_launch_count(self._h))
+
+    def cta_clocks(self):
+        out = np.zeros(self.n_rep, dtype=np.uint64)
+        _check(self._L.nm_get_cta_clocks(self._h, _ptr(out)))
+        return out
 
 
 # ----------------------------------------------------------------------------- a-14 RDF

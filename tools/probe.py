@@ -8,12 +8,14 @@ from oracle import oracle as orc
 def grid(n_side, np_, nt):
     n = 4 * n_side ** 3
     P = np.linspace(1, 8, np_, dtype=np.float32).astype(float)
-    T = np.linspace(0.25, 2.5, nt, dtype=np.float32).astype(float)
+    import os
+    tlo, thi = float(os.environ.get('TLO', 0.25)), float(os.environ.get('THI', 2.5))
+    T = np.linspace(tlo, thi, nt, dtype=np.float32).astype(float)
     rng = np.random.default_rng(0)
     xs, boxes, et, pf, tt = [], [], [], [], []
     for i in range(np_):
         for j in range(nt):
-            rho = 1.05 - 0.35 * (T[j] - 0.25) / 2.25 + 0.02 * (P[i] - 1)
+            rho = min(1.1, 1.05 - 0.35 * (T[j] - 0.25) / 2.25 + 0.02 * (P[i] - 1))
             box = n_side * (4 / rho) ** (1 / 3)
             x = orc.fcc_positions(n_side, box) + rng.normal(0, 0.03, (n, 3))
             xs.append(orc.wrap(x.reshape(-1), box)); boxes.append(box); et.append(T[j]); pf.append(P[i] / T[j]); tt.append(T[j])
@@ -46,8 +48,11 @@ def main():
         print("cycle %d: %.1f ms  atom-steps/s %.3e  sweeps/s %.3e  pair-flops %.2f TF/s  builds %d evals %d  listpairs/inpairs %.2f swaps %d  <ah> %.2f <av> %.2f <ap> %.2f" % (
             cyc, dt * 1e3, ct["hmc_atom_steps"] / dt, ct["sweeps"] / dt, flops / dt / 1e12, ct["list_builds"], ct["force_evals"],
             ct["list_pairs"] / max(1, ct["pairs_force"] + ct["pairs_full"]), sw, th[:, 17].mean(), th[:, 16].mean(), th[:, 15].mean()))
-        print("   per-call clk: outer %.0f inner %.0f vel %.0f | share outer %.2f inner %.2f vel %.2f" % (ct["clk_outer"] / max(1, ct["outer_builds"]), ct["clk_inner"] / max(1, ct["list_builds"]), ct["clk_vel"] / max(1, ct["hmc_moves"]), ct["clk_outer"] / ct["clk_total"], ct["clk_inner"] / ct["clk_total"], ct["clk_vel"] / ct["clk_total"]))
+        print("   per-call clk: outer %.0f inner %.0f vel %.0f | share outer %.2f inner %.2f vel %.2f" % (ct["clk_outer"] / max(1, ct["outer_builds"] or ct["list_builds"]), ct["clk_inner"] / max(1, ct["list_builds"]), ct["clk_vel"] / max(1, ct["hmc_moves"]), ct["clk_outer"] / ct["clk_total"], ct["clk_inner"] / ct["clk_total"], ct["clk_vel"] / ct["clk_total"]))
         print("   outer builds %d | clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["outer_builds"], ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
+    clk = eng.cta_clocks().astype(float).reshape(np_, nt) / 1e6
+    print("per-slot Mclk by temperature (mean over P):", np.round(clk.mean(0), 1))
+    print("per-slot Mclk min %.1f mean %.1f max %.1f" % (clk.min(), clk.mean(), clk.max()))
     print("T col0 thermo:", np.round(th[:nt, :6], 3)[::max(1, nt // 4)])
 
 main()
