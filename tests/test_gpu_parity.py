@@ -256,3 +256,110 @@ def test_rdf_large_sample_property(nm, orc):
     got = nm.rdf_counts(pos, np.array([box, box]), r)
     np.testing.assert_array_equal(got[0], got[1])
     np.testing.assert_array_equal(got[0], orc.rdf_counts(pos[0], box, r))
+
+
+# ------------------------------------------------------------------ (e) sharding: N ranks == 1 rank
+def test_row_sharded_engines_reproduce_the_single_engine_run(nm, orc):
+    """two engines holding two pressure rows each (what two ranks hold) give bit-identical thermo, states and swap
+    permutations to one engine holding all four rows: the RNG is keyed on the GLOBAL slot, exchanges are row-local"""
+    import torch
+    np_, nt, n = 4, 3, 256
+    ns = np_ * nt
+    x, box = _configs(orc, 4, list(np.linspace(1.1, 0.75, ns)), [0.05] * ns, seed=31)
+    box = np.array([orc.round6(b) for b in box])
+    T = np.tile(np.linspace(0.6, 1.8, nt), np_)
+    P = np.repeat(np.linspace(1.0, 6.0, np_), nt)
+    et, pf = T.copy(), P / T
+    kw = dict(natoms=n, nt=nt, mod=10, bulk_move=True, seed=77)
+
+    def drive(engines, offs):
+        th_all, perms = [], []
+        for cyc in range(3):
+            for e in engines:
+                e.run_cycle(cyc)
+            th = np.concatenate([e.get_thermo() for e in engines])
+            for e in engines:
+                e.adapt()
+            # the all-gather: every engine packs its slots, the tables are concatenated in rank order
+            parts = []
+            for e in engines:
+                t = torch.empty((e.n_rep, 2), dtype=torch.float64, device="cuda")
+                e.exchange_pack(t.data_ptr())
+                parts.append(t)
+            table = torch.cat(parts)
+            out = [e.exchange_apply(table.data_ptr(), et, pf, cyc) for e in engines]
+            assert all(np.array_equal(out[0][0], o[0]) and out[0][1] == o[1] for o in out)
+            th_all.append(th); perms.append(out[0][0])
+        st = [e.get_state() for e in engines]
+        return np.array(th_all), np.array(perms), {k: np.concatenate([s[k] for s in st]) for k in st[0]}
+
+    def make(n_rep, off):
+        e = nm.Engine(n_rep=n_rep, n_rep_global=ns, rep_offset=off, **kw)
+        sl = slice(off, off + n_rep)
+        e.set_labels(et[sl], pf[sl], T[sl])
+        e.set_state(x=x[sl], v=np.zeros_like(x[sl]), box=box[sl], dx=np.full(n_rep, .03125), dv=np.full(n_rep, .03125),
+                    dt=np.full(n_rep, .00390625))
+        return e
+
+    one = [make(ns, 0)]
+    th1, p1, s1 = drive(one, [0])
+    two = [make(ns // 2, 0), make(ns // 2, ns // 2)]
+    th2, p2, s2 = drive(two, [0, ns // 2])
+    for e in one + two:
+        e.close()
+    np.testing.assert_array_equal(p1, p2)
+    np.testing.assert_array_equal(th1, th2)
+    for k in s1:
+        np.testing.assert_array_equal(s1[k], s2[k])
+
+
+# ------------------------------------------------------------------ ensemble averages (north star: within 2 sigma)
+def test_ensemble_averages_agree_with_oracle(nm, orc):
+    """independent chains (different seeds) on the GPU and in the oracle sample the same NPT ensemble: <pe>, <vol> and the
+    HMC / VMC acceptance agree within 2 sigma (sigma from the spread over independent chains, block-averaged)"""
+    n_side, n, nrep = 4, 256, 8
+    T0, P0 = 1.4, 2.0                              # LJ liquid, well away from the melting line
+    x, box = _configs(orc, n_side, [0.78] * nrep, [0.1] * nrep, seed=41)
+    box = np.array([orc.round6(b) for b in box])
+    labels = np.tile(np.array([T0, P0 / T0, T0, orc.round6(T0)]), (nrep, 1))
+    mod, nequil, nprod = 16, 40, 60
+
+    def chain_stats(th_list):
+        th = np.array(th_list)                      # (cycle, replica, 18)
+        pe, vol = th[:, :, 1].mean(0), th[:, :, 5].mean(0)
+        ah = th[:, :, 14].sum(0) / np.maximum(th[:, :, 13].sum(0), 1)
+        av = th[:, :, 12].sum(0) / np.maximum(th[:, :, 11].sum(0), 1)
+        return np.stack([pe, vol, ah, av], 1)       # per independent chain
+
+    # every replica is an independent chain at the same state point; step sizes fixed (no adaptation) so that
+    # both sides sample with identical proposal distributions
+    with nm.Engine(natoms=n, n_rep=nrep, nt=nrep, mod=mod, bulk_move=True, seed=1001) as eng:
+        eng.set_labels(*labels.T)
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(nrep, .01), dv=np.full(nrep, .02), dt=np.full(nrep, .004))
+        g = []
+        for cyc in range(nequil + nprod):
+            eng.run_cycle(cyc)
+            th = eng.get_thermo()
+            if cyc >= nequil:
+                g.append(th)
+            eng.set_state(dx=np.full(nrep, .01), dv=np.full(nrep, .02), dt=np.full(nrep, .004))   # keep counters per cycle
+            eng.adapt()
+            eng.set_state(dx=np.full(nrep, .01), dv=np.full(nrep, .02), dt=np.full(nrep, .004))
+    params = orc.make_params(mod=mod, bulk_move=1, seed=2002)
+    xo, vo = x.copy(), np.zeros_like(x)
+    scal = np.stack([box, np.full(nrep, .01), np.full(nrep, .02), np.full(nrep, .004)], 1).copy()
+    counts = np.zeros((nrep, 6))
+    o = []
+    for cyc in range(nequil + nprod):
+        rows = []
+        for k in range(nrep):
+            th, _ = orc.cycle(params, labels[k], k, cyc, xo[k], vo[k], scal[k], counts[k])
+            rows.append(th)
+            counts[k] = 0
+        if cyc >= nequil:
+            o.append(np.array(rows))
+    sg, so = chain_stats(g), chain_stats(o)
+    for col, name in enumerate(["pe", "vol", "hmc acceptance", "vmc acceptance"]):
+        mg, mo = sg[:, col].mean(), so[:, col].mean()
+        sem = np.sqrt(sg[:, col].var(ddof=1) / nrep + so[:, col].var(ddof=1) / nrep)
+        assert abs(mg - mo) <= 2.0 * sem, "%s: gpu %.5g oracle %.5g sem %.3g" % (name, mg, mo, sem)
