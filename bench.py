@@ -28,6 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one nm::k_cycle launch from the committed `ncu --set full` capture
+# (profiles/r1_cycle_c2_ncu_full.txt); per workload, None where no capture exists
+NCU_TRAFFIC_BYTES = {"c2": 54.970368e6 + 901.335296e6}
+
 WORKLOADS = {
     # name: (supercell, pressure rows per GPU, temperatures, bulk_move, ppos, pvol, mod, description)
     "c1": (4, 8, 8, True, 0.125, 0.125, 128, "C1: LJ fcc 4x4x4 (256 atoms), 8x8 P-T grid per GPU, default move mix"),
@@ -220,7 +224,8 @@ def run_b200(args):
                     "steps": e2e_steps, "note": "set_state (pinned host x, v, box, step sizes) -> cycle -> get_thermo + get_state, every step"},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "fp64_fma", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "nm::k_cycle", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if comm.world == 1 else None, "traffic_unit": "bytes/launch (ncu capture, profiles/r1_cycle_c2_ncu_full.txt)",
+                         "kernel": "nm::k_cycle", "kernel_ms_per_step": kernel_ms / args.steps,
                          "peak_source": "live DFMA microbenchmark (nm_measure_fma_peak); MEASURED_PEAKS.json carries no FP64 figure",
                          "flops": "24/in-cutoff pair (force), 30 (force+energy+virial), 13/neighbour of a single-atom dE, 18/atom-step",
                          "in_cutoff_pairs_per_step": inpairs / args.steps, "listed_over_in_cutoff": listpairs / max(1.0, inpairs),
