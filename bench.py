@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--equil", type=int, default=4, help="untimed equilibration cycles before the warm-up")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="pair arithmetic: 64 (headline) or the FP32 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     return ap.parse_args()
@@ -136,7 +137,7 @@ def run_b200(args):
     x, v, box = initial_states(P[comm.rank * rows:(comm.rank + 1) * rows], T, sz, dev, 1000 + comm.rank)
     stream = torch.cuda.current_stream().cuda_stream
     eng = nm.Engine(natoms=natoms, n_rep=nloc, nt=nt, n_rep_global=ns, rep_offset=off, device=dev, mod=mod, bulk_move=bulk,
-                    ppos=ppos, pvol=pvol, seed=remcmc.SEED, stream=stream)
+                    ppos=ppos, pvol=pvol, seed=remcmc.SEED, stream=stream, precision=args.precision)
     sl = slice(off, off + nloc)
     eng.set_labels(et[sl], pf[sl], temp[sl])
     eng.set_state(x=x, v=v, box=box, dx=np.full(nloc, 0.03125), dv=np.full(nloc, 0.03125), dt=np.full(nloc, 0.00390625))
@@ -209,13 +210,13 @@ def run_b200(args):
     atom_steps, sweeps, flops, atom_steps_e2e, launches_all, inpairs, listpairs, builds, obuilds = (float(t) for t in work.cpu())
     out = None
     if comm.rank == 0:
-        peak, _ = nm.measure_fma_peak(dev, 64)
+        peak, _ = nm.measure_fma_peak(dev, args.precision)
         achieved = flops / comm.world / (kernel_ms * 1e-3) if kernel_ms > 0 else 0.0      # per-GPU, kernel-only time
         out = {
             "metric": "hmc_atom_steps_per_sec", "value": atom_steps / (ms * 1e-3), "unit": "atom-steps/s",
             "mc_sweeps_per_sec": sweeps / (ms * 1e-3),
             "n_gpus": comm.world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
             "data": "synthetic: pressure-relaxed fcc + random displacement (the reference's init_sample), %d equilibration cycles, counter-based RNG seed 256" % args.equil,
             "config": {"workload": desc, "natoms": natoms, "replicas_per_gpu": nloc, "grid": [npn, nt], "moves_per_cycle": mod,
                        "hmc_steps": 8, "l2": "inputs larger than L2 (per-GPU state + neighbour lists of %d replicas > 126 MB)" % nloc if nloc * natoms > 60000 else "working set fits L2; no flush (compute-bound on-chip kernel)",
@@ -223,7 +224,7 @@ def run_b200(args):
             "e2e": {"value": atom_steps_e2e / (e2e_ms * 1e-3), "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "note": "set_state (pinned host x, v, box, step sizes) -> cycle -> get_thermo + get_state, every step"},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "fp64_fma", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
+            "roofline": {"bound": "fp64_fma" if args.precision == 64 else "fp32_fma", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if comm.world == 1 else None, "traffic_unit": "bytes/launch (ncu capture, profiles/r1_cycle_c2_ncu_full.txt)",
                          "kernel": "nm::k_cycle", "kernel_ms_per_step": kernel_ms / args.steps,
                          "peak_source": "live DFMA microbenchmark (nm_measure_fma_peak); MEASURED_PEAKS.json carries no FP64 figure",

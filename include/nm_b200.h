@@ -55,7 +55,7 @@ enum nm_thermo_col {
 
 /* counters returned by nm_get_counters (uint64 each, summed over local replicas
  * since nm_create or the last nm_reset_counters) */
-#define NM_COUNTER_WIDTH 20
+#define NM_COUNTER_WIDTH 22
 enum nm_counter_col {
   NM_CT_SWEEPS = 0,        /* move_mc calls (lammps_remcmc.py:677-679)            */
   NM_CT_HMC_MOVES,         /* hamiltonian_mc calls                                */
@@ -76,7 +76,9 @@ enum nm_counter_col {
   NM_CT_CLK_OUTER,         /* SM clocks in outer builds                           */
   NM_CT_CLK_INNER,         /* SM clocks in inner builds                           */
   NM_CT_CLK_VEL,           /* SM clocks in the HMC velocity draw                  */
-  NM_CT_RESERVED
+  NM_CT_RESERVED,
+  NM_CT_DBG_LOOPCLK,       /* diagnostics: clocks thread 0 spent in its own pair loop (first atom)  */
+  NM_CT_DBG_LOOPIT         /* diagnostics: quad iterations of that loop                             */
 };
 
 typedef struct nm_engine nm_engine;   /* opaque */

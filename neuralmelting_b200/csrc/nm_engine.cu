@@ -32,6 +32,7 @@ struct Dev {
   int N, Npad, nrep, nrep_global, rep_offset, nt, maxq, maxqo, maxnbo;   // inner / outer list capacity in quads, outer scratch entries
   int nstps, mod, bulk, text_rounding;
   int nsm, per_sm;                         // SM count and CTAs that fit per SM (cost-balanced placement)
+  int f32;                                 // precision = 32: pair arithmetic in FP32 on the fractional float copies
   int small;                               // 1: N <= NSMALL: single-level list built from an all-pairs hit matrix in shared memory
   double ppos, pvol, lat, mass, rc, skin, oskin;
   uint32_t seed_lo, seed_hi;
@@ -615,6 +616,7 @@ __device__ __forceinline__ void sync_and_maybe_build(const Dev& d, Ctx& cx, int 
     cx.sht[3 * c] = (c / 9 - 1) * cx.L; cx.sht[3 * c + 1] = ((c / 3) % 3 - 1) * cx.L; cx.sht[3 * c + 2] = (c % 3 - 1) * cx.L;
   }
   if (__syncthreads_or(flag)) build_list(d, cx);
+  if (d.f32) { wrap_and_refresh(cx, false); __syncthreads(); }   // FP32 mode: the force loop reads the float copies
 }
 // generic pass: is every atom still inside the displacement budget?
 __device__ void check_list(const Dev& d, Ctx& cx) {
@@ -692,7 +694,11 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
     for (int q = 0; q < nq; q++) {
       // the quad two iterations ahead is pulled into L1 (no register cost); the next one is loaded here
       if (q + 2 < nq) asm volatile("prefetch.global.L1 [%0];" :: "l"(lp + (size_t)(q + 2) * Npad));
+#ifdef NM_EXPERIMENT_NOLIST
+      const ushort4 nxt = cur;
+#else
       const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
+#endif
       double xs = xi, ys = yi, zs = zi;
       if (!MIC) {
         const int code = (cur.x >> 13) | ((cur.y >> 13) << 3);
@@ -704,6 +710,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       lj_pair<EW, MIC>(cx.sp + 3 * cur.w, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       cur = nxt;
     }
+    if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_eval0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
     cx.gf[i] = fx; cx.gf[Npad + i] = fy; cx.gf[2 * Npad + i] = fz;
     if (KICK) {
       const double vx = fma(dtf, fx, cx.gv[i]), vy = fma(dtf, fy, cx.gv[Npad + i]), vz = fma(dtf, fz, cx.gv[2 * Npad + i]);
@@ -728,9 +735,79 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
                             cx.ct[NM_CT_CLK_EVAL] += (unsigned long long)(clock64() - t_eval0); }
   }
 }
+// FP32 mode (nm_config.precision = 32; tolerance 1e-5 relative): the pair arithmetic runs on the FP32 pipe from the
+// float32 FRACTIONAL copies of the positions (one 16-byte gather per pair), image shifts are -1/0/+1 in box units,
+// forces are accumulated per atom in float and scaled by L at the end; energy / virial partial sums are per-thread
+// floats reduced in double. State, integration and Metropolis arithmetic stay FP64.
+template <bool EW, bool KICK, bool MIC>
+__device__ void eval_forces_f32(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
+  const int N = cx.N, Npad = cx.Npad;
+  const float Lf = (float)cx.L, L2f = Lf * Lf, rc2f = (float)(d.rc * d.rc), magic = 12582912.f;
+  float e = 0.f, vir = 0.f; double ke = 0.0; int np = 0;
+  const long long t_eval0 = clock64();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 pi = cx.sf[i];
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    const int nq = cx.nnb[i];
+    const ushort4* lp = cx.list + i;
+    ushort4 cur = nq > 0 ? lp[0] : make_ushort4(0, 0, 0, 0);
+    for (int q = 0; q < nq; q++) {
+      if (q + 2 < nq) asm volatile("prefetch.global.L1 [%0];" :: "l"(lp + (size_t)(q + 2) * Npad));
+      const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
+      float xs = pi.x, ys = pi.y, zs = pi.z;
+      if (!MIC) {
+        const int code = (cur.x >> 13) | ((cur.y >> 13) << 3);
+        xs -= (float)(code / 9 - 1); ys -= (float)((code / 3) % 3 - 1); zs -= (float)(code % 3 - 1);
+      }
+      const int jj[4] = { cur.x & 0x1fff, cur.y & 0x1fff, cur.z, cur.w };
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const float4 pj = cx.sf[jj[t]];
+        float dx = xs - pj.x, dy = ys - pj.y, dz = zs - pj.z;
+        if (MIC) { dx -= __fadd_rn(__fadd_rn(dx, magic), -magic); dy -= __fadd_rn(__fadd_rn(dy, magic), -magic); dz -= __fadd_rn(__fadd_rn(dz, magic), -magic); }
+        const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) * L2f;
+        const bool in = rsq < rc2f;
+        const float r2inv = __frcp_rn(rsq);
+        const float r6inv = r2inv * r2inv * r2inv;
+        const float fpair = in ? r6inv * fmaf(48.f, r6inv, -24.f) * r2inv : 0.f;
+        fx = fmaf(dx, fpair, fx); fy = fmaf(dy, fpair, fy); fz = fmaf(dz, fpair, fz);
+        np += in;
+        if (EW) { e += in ? r6inv * fmaf(4.f, r6inv, -4.f) : 0.f; vir = fmaf(rsq, fpair, vir); }
+      }
+      cur = nxt;
+    }
+    const double Fx = (double)(fx * Lf), Fy = (double)(fy * Lf), Fz = (double)(fz * Lf);
+    cx.gf[i] = Fx; cx.gf[Npad + i] = Fy; cx.gf[2 * Npad + i] = Fz;
+    if (KICK) {
+      const double vx = fma(dtf, Fx, cx.gv[i]), vy = fma(dtf, Fy, cx.gv[Npad + i]), vz = fma(dtf, Fz, cx.gv[2 * Npad + i]);
+      cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+      if (EW) ke += vx * vx + vy * vy + vz * vz;
+    }
+  }
+  if (EW) {
+    double r[4] = { 0.5 * (double)e, 0.5 * (double)vir, (double)np, ke };
+    block_sum<4>(r, cx.red);
+    out[0] = r[0]; out[1] = r[1]; out[2] = 0.5 * r[2]; out[3] = 0.5 * d.mass * r[3];
+    if (threadIdx.x == 0) {
+      cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_PAIRS_FULL] += (unsigned long long)out[2];
+      cx.ct[NM_CT_LIST_PAIRS] += (unsigned long long)cx.list_pairs;
+      cx.ct[NM_CT_CLK_EVAL] += (unsigned long long)(clock64() - t_eval0);
+    }
+  } else {
+    np = __reduce_add_sync(0xffffffffu, np);
+    if ((threadIdx.x & 31) == 0) atomicAdd(cx.s_pairs, (unsigned long long)np);
+    __syncthreads();
+    if (threadIdx.x == 0) { cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_LIST_PAIRS] += (unsigned long long)cx.list_pairs;
+                            cx.ct[NM_CT_CLK_EVAL] += (unsigned long long)(clock64() - t_eval0); }
+  }
+}
+
 template <bool EW, bool KICK>
 __device__ __forceinline__ void eval_forces(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
-  if (cx.mic) eval_forces_t<EW, KICK, true>(d, cx, dtf, out);
+  if (d.f32) {
+    if (cx.mic) eval_forces_f32<EW, KICK, true>(d, cx, dtf, out);
+    else eval_forces_f32<EW, KICK, false>(d, cx, dtf, out);
+  } else if (cx.mic) eval_forces_t<EW, KICK, true>(d, cx, dtf, out);
   else eval_forces_t<EW, KICK, false>(d, cx, dtf, out);
 }
 
@@ -1322,7 +1399,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   if (cfg->natoms < 2 || cfg->natoms > 8000) return fail(NM_EINVAL, "nm_create: natoms %d out of range [2, 8000] (13-bit neighbour indices; shared memory holds ~5000 atoms)", cfg->natoms);
   if (cfg->n_rep < 1 || cfg->nt < 1 || cfg->n_rep % cfg->nt || cfg->rep_offset % cfg->nt || cfg->n_rep_global < cfg->rep_offset + cfg->n_rep)
     return fail(NM_EINVAL, "nm_create: local slots must be whole pressure rows (n_rep=%d rep_offset=%d nt=%d global=%d)", cfg->n_rep, cfg->rep_offset, cfg->nt, cfg->n_rep_global);
-  if (cfg->precision != 64 && cfg->precision != 0) return fail(NM_EINVAL, "nm_create: precision %d not available in this build (64 only)", cfg->precision);
+  if (cfg->precision != 64 && cfg->precision != 32 && cfg->precision != 0) return fail(NM_EINVAL, "nm_create: precision must be 64 or 32 (got %d)", cfg->precision);
   if (cfg->nstps < 1 || cfg->mod < 0 || cfg->ppos < 0 || cfg->pvol < 0 || cfg->ppos + cfg->pvol > 1.0 + 1e-12) return fail(NM_EINVAL, "nm_create: bad move parameters");
   if (!(cfg->rc > 0) || !(cfg->mass > 0)) return fail(NM_EINVAL, "nm_create: rc and mass must be positive");
   int ndev = nm_device_count();
@@ -1359,6 +1436,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     d.maxqo = ((maxnbo + 3) / 4 + 8 + 1) & ~1;
   }
   h->threads = N <= 256 ? 256 : (N <= 512 ? 512 : 1024);   // 64 registers/thread: 32 warps per SM hide the FP64 latency
+  d.f32 = cfg->precision == 32;
   d.small = N <= NSMALL;
   h->smem = smem_bytes(d.Npad, N, d.small);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, cfg->device) == cudaSuccess) h->nsm = pr.multiProcessorCount; else h->nsm = 148; }

@@ -363,3 +363,39 @@ def test_ensemble_averages_agree_with_oracle(nm, orc):
         mg, mo = sg[:, col].mean(), so[:, col].mean()
         sem = np.sqrt(sg[:, col].var(ddof=1) / nrep + so[:, col].var(ddof=1) / nrep)
         assert abs(mg - mo) <= 2.0 * sem, "%s: gpu %.5g oracle %.5g sem %.3g" % (name, mg, mo, sem)
+
+
+# ------------------------------------------------------------------ FP32 mode (north star: 1e-5 relative)
+@pytest.mark.parametrize("n_side", [4, 5, 10])
+def test_fp32_mode_eval_within_1e5(nm, orc, n_side):
+    rho = [1.122, 1.1, 0.9, 0.6]
+    sig = [0.0, 0.05, 0.12, 0.18]            # physical configurations (no near-overlaps: r^-13 amplifies float32 positions)
+    x, box = _configs(orc, n_side, rho, sig, seed=50 + n_side)
+    n = 4 * n_side ** 3
+    with nm.Engine(natoms=n, n_rep=len(box), nt=len(box), precision=32) as eng:
+        eng.set_state(x=x, box=box)
+        pe, w, f, npairs = eng.eval()
+    for k in range(len(box)):
+        pe_o, w_o, f_o, np_o = orc.lj_eval_list(x[k], box[k])
+        assert abs(npairs[k] - np_o) <= 2                      # a pair within float rounding of the cutoff may flip
+        assert abs(pe[k] - pe_o) <= 1e-5 * abs(pe_o)
+        assert abs(w[k] - w_o) <= 1e-5 * max(abs(w_o), abs(pe_o))
+        # forces: relative to the pair-force scale; net forces cancel in a crystal, so the scale is max |f| or
+        # (a lower bound of) the per-atom sum of pair-force magnitudes, 6 |W| / N
+        assert np.abs(f[k] - f_o).max() <= 1e-5 * max(np.abs(f_o).max(), 6.0 * abs(w_o) / n, 1.0)
+
+
+def test_fp32_mode_cycle_tracks_fp64(nm, orc):
+    """same RNG streams: the FP32-mode chain makes the same accept decisions as the FP64 chain over a short run and its
+    thermo stays within FP32 accuracy of it"""
+    x, box = _configs(orc, 4, [1.05, 0.8], [0.05, 0.05], seed=61)
+    box = np.array([orc.round6(b) for b in box])
+    out = {}
+    for prec in (64, 32):
+        with nm.Engine(natoms=256, n_rep=2, nt=2, mod=12, bulk_move=True, precision=prec, seed=9) as eng:
+            eng.set_labels([0.7, 1.5], [2.0 / 0.7, 2.0 / 1.5], [0.7, 1.5])
+            eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[.03, .03], dv=[.03, .03], dt=[.004, .004])
+            eng.run_cycle(0)
+            out[prec] = eng.get_thermo()
+    np.testing.assert_array_equal(out[32][:, 9:15], out[64][:, 9:15])
+    np.testing.assert_allclose(out[32][:, :6], out[64][:, :6], rtol=2e-4)

@@ -1,5 +1,5 @@
 """ad-hoc timing probe (development aid, not the benchmark)"""
-import sys, time
+import os, sys, time
 import numpy as np
 sys.path.insert(0, ".")
 from neuralmelting_b200 import engine as nm
@@ -32,7 +32,7 @@ def main():
     for prec in (64, 32):
         fl, ms = nm.measure_fma_peak(0, prec)
         print("fma peak fp%d: %.2f TFLOP/s (%.3f ms)" % (prec, fl / 1e12, ms))
-    eng = nm.Engine(natoms=n, n_rep=ns, nt=nt, bulk_move=bool(bulk), skin=skin, skin_outer=oskin)
+    eng = nm.Engine(natoms=n, n_rep=ns, nt=nt, bulk_move=bool(bulk), skin=skin, skin_outer=oskin, precision=int(os.environ.get('PREC', 64)))
     eng.set_labels(et, pf, tt)
     t0 = time.time()
     eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(ns, .03125), dv=np.full(ns, .03125), dt=np.full(ns, .00390625))
@@ -49,6 +49,7 @@ def main():
             cyc, dt * 1e3, ct["hmc_atom_steps"] / dt, ct["sweeps"] / dt, flops / dt / 1e12, ct["list_builds"], ct["force_evals"],
             ct["list_pairs"] / max(1, ct["pairs_force"] + ct["pairs_full"]), sw, th[:, 17].mean(), th[:, 16].mean(), th[:, 15].mean()))
         print("   per-call clk: outer %.0f inner %.0f vel %.0f | share outer %.2f inner %.2f vel %.2f" % (ct["clk_outer"] / max(1, ct["outer_builds"] or ct["list_builds"]), ct["clk_inner"] / max(1, ct["list_builds"]), ct["clk_vel"] / max(1, ct["hmc_moves"]), ct["clk_outer"] / ct["clk_total"], ct["clk_inner"] / ct["clk_total"], ct["clk_vel"] / ct["clk_total"]))
+        print("   thread0 pair loop: %.0f clk per quad-iteration, %.1f quads/eval, loop %.0f clk/eval" % (ct["dbg_loopclk"] / max(1, ct["dbg_loopit"]), ct["dbg_loopit"] / max(1, ct["force_evals"]), ct["dbg_loopclk"] / max(1, ct["force_evals"])))
         print("   outer builds %d | clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["outer_builds"], ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
     clk = eng.cta_clocks().astype(float).reshape(np_, nt) / 1e6
     print("per-slot Mclk by temperature (mean over P):", np.round(clk.mean(0), 1))
