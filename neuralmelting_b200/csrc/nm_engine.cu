@@ -694,11 +694,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
     for (int q = 0; q < nq; q++) {
       // the quad two iterations ahead is pulled into L1 (no register cost); the next one is loaded here
       if (q + 2 < nq) asm volatile("prefetch.global.L1 [%0];" :: "l"(lp + (size_t)(q + 2) * Npad));
-#ifdef NM_EXPERIMENT_NOLIST
-      const ushort4 nxt = cur;
-#else
       const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
-#endif
       double xs = xi, ys = yi, zs = zi;
       if (!MIC) {
         const int code = (cur.x >> 13) | ((cur.y >> 13) << 3);

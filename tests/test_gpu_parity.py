@@ -369,7 +369,7 @@ def test_ensemble_averages_agree_with_oracle(nm, orc):
 @pytest.mark.parametrize("n_side", [4, 5, 10])
 def test_fp32_mode_eval_within_1e5(nm, orc, n_side):
     rho = [1.122, 1.1, 0.9, 0.6]
-    sig = [0.0, 0.05, 0.12, 0.18]            # physical configurations (no near-overlaps: r^-13 amplifies float32 positions)
+    sig = [0.0, 0.05, 0.10, 0.12]            # physical configurations (no near-overlaps: r^-13 amplifies float32 positions)
     x, box = _configs(orc, n_side, rho, sig, seed=50 + n_side)
     n = 4 * n_side ** 3
     with nm.Engine(natoms=n, n_rep=len(box), nt=len(box), precision=32) as eng:
