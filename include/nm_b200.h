@@ -197,6 +197,14 @@ int  nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs,
                    const float* pos, const float* box, int32_t natoms, int64_t nsamples,
                    const double* edges, int32_t nbins, uint32_t* counts);
 
+/* ---- N1 (next row): calculate_cdf (lammps_distr.py:161-171) over a batch of samples.
+ *   edges : HOST float64 [3][nb+1] (RV = linspace(0, l, CBINS+1) - l/2 per axis, lammps_distr.py:109-111)
+ *   counts: uint32 [nsamples][nb][nb][nb], the reference's cd before '/natoms' (sum over the 27 images of
+ *           np.histogramdd of the float32 pair vectors). nb <= 32. Bit-exact like nm_rdf_counts. */
+int  nm_cdf_counts(int device, void* cuda_stream, int dev_ptrs,
+                   const float* pos, const float* box, int32_t natoms, int64_t nsamples,
+                   const double* edges, int32_t nb, uint32_t* counts);
+
 /* ---- a-13: native '%.4E' text records (write_thrm / write_traj,
  *      lammps_remcmc.py:235-256). Pure host code; returns bytes written or <0.
  *      buf may be NULL to query the size. */

@@ -182,3 +182,144 @@ done:
 
   return rc;
 }
+
+// =================================================================== N1: Cartesian pair-vector density
+// calculate_cdf (lammps_distr.py:161-171): for each of the 27 image vectors, np.histogramdd of the float32 pair
+// vectors dvm[b, a, :] = pos_a - (pos_b + box*s) on the float64 edges rv (three rows of nb+1 edges). Bit-exact:
+// same float32 operation sequence as the RDF kernel, float32 thresholds exactly equivalent to the float64 edge
+// tests of np.searchsorted(side='right') with the right-most edge closed, outliers dropped.
+namespace nmcdf {
+
+constexpr int T = 256;
+
+struct CdfParams {
+  const float* pos; const float* box; uint32_t* counts;
+  const float* thr;            // [3][nb+1] lower thresholds, thr[d][k]: (double)x >= edge[d][k]  <=>  x >= thr[d][k]
+  int N, nb, a_chunk;
+  float t_top[3], inv_d[3];    // x <= t_top[d] <=> (double)x <= edge[d][nb]
+};
+
+// bin of x along one axis, or -1 when outside [edge[0], edge[nb]]
+__device__ __forceinline__ int bin1(float x, const float* t, int nb, float t_top, float inv_d) {
+  if (!(x >= t[0] && x <= t_top)) return -1;
+  int k = (int)((x - t[0]) * inv_d);
+  k = max(0, min(k, nb));
+  while (k > 0 && x < t[k]) k--;
+  while (k < nb && x >= t[k + 1]) k++;
+  return k == nb ? nb - 1 : k;       // the right-most edge belongs to the last bin
+}
+
+__global__ void __launch_bounds__(T) k_cdf(CdfParams p) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* ax = reinterpret_cast<float*>(sm);
+  float* ay = ax + p.a_chunk; float* az = ay + p.a_chunk;
+  float* sthr = az + p.a_chunk;                       // 3 * (nb + 1)
+  uint32_t* hist = reinterpret_cast<uint32_t*>(sthr + 3 * (p.nb + 1));
+  const int nb = p.nb, nb3 = nb * nb * nb;
+  const int s = blockIdx.y, a0 = blockIdx.x * p.a_chunk, na = min(p.N, a0 + p.a_chunk) - a0;
+  const float* ps = p.pos + (size_t)s * p.N * 3;
+  for (int a = threadIdx.x; a < na; a += T) { ax[a] = ps[3 * (a0 + a)]; ay[a] = ps[3 * (a0 + a) + 1]; az[a] = ps[3 * (a0 + a) + 2]; }
+  for (int k = threadIdx.x; k < 3 * (nb + 1); k += T) sthr[k] = p.thr[k];
+  for (int k = threadIdx.x; k < nb3; k += T) hist[k] = 0u;
+  __syncthreads();
+  const float* tx = sthr; const float* ty = sthr + (nb + 1); const float* tz = sthr + 2 * (nb + 1);
+  const float bx = p.box[s], nbx = __fmul_rn(bx, -1.0f);
+  for (int b = threadIdx.x; b < p.N; b += T) {
+    const float px = ps[3 * b], py = ps[3 * b + 1], pz = ps[3 * b + 2];
+    const float im[3][3] = { { __fadd_rn(px, nbx), px, __fadd_rn(px, bx) }, { __fadd_rn(py, nbx), py, __fadd_rn(py, bx) },
+                             { __fadd_rn(pz, nbx), pz, __fadd_rn(pz, bx) } };
+    for (int a = 0; a < na; a++) {
+      const float q[3] = { ax[a], ay[a], az[a] };
+      int bins[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        bins[0][i] = bin1(__fsub_rn(q[0], im[0][i]), tx, nb, p.t_top[0], p.inv_d[0]);
+        bins[1][i] = bin1(__fsub_rn(q[1], im[1][i]), ty, nb, p.t_top[1], p.inv_d[1]);
+        bins[2][i] = bin1(__fsub_rn(q[2], im[2][i]), tz, nb, p.t_top[2], p.inv_d[2]);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) if (bins[0][i] >= 0)
+#pragma unroll
+        for (int j = 0; j < 3; j++) if (bins[1][j] >= 0)
+#pragma unroll
+          for (int k = 0; k < 3; k++) if (bins[2][k] >= 0)
+            atomicAdd(&hist[(bins[0][i] * nb + bins[1][j]) * nb + bins[2][k]], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t* out = p.counts + (size_t)s * nb3;
+  for (int k = threadIdx.x; k < nb3; k += T) if (hist[k]) atomicAdd(&out[k], hist[k]);
+}
+
+}  // namespace nmcdf
+
+extern "C" int nm_cdf_counts(int device, void* cuda_stream, int dev_ptrs, const float* pos, const float* box,
+                             int32_t natoms, int64_t nsamples, const double* edges, int32_t nb, uint32_t* counts) {
+  using namespace nmcdf;
+  if (!pos || !box || !edges || !counts) return nm_fail_msg(NM_EINVAL, "nm_cdf_counts: null argument");
+  if (natoms < 1 || nsamples < 0 || nb < 1 || nb > 32) return nm_fail_msg(NM_EINVAL, "nm_cdf_counts: bad sizes (natoms=%d nsamples=%lld bins=%d; at most 32 bins per axis)", natoms, (long long)nsamples, nb);
+  for (int d = 0; d < 3; d++) for (int k = 1; k <= nb; k++)
+    if (!(edges[d * (nb + 1) + k] > edges[d * (nb + 1) + k - 1])) return nm_fail_msg(NM_EINVAL, "nm_cdf_counts: edges must increase strictly");
+  if (nsamples == 0) return NM_OK;
+  int ndev = nm_device_count();
+  if (ndev < 0) return ndev;
+  if (device < 0 || device >= ndev) return nm_fail_msg(NM_ENODEV, "nm_cdf_counts: device %d not in [0,%d)", device, ndev);
+  int rc = NM_OK;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  float *d_pos = nullptr, *d_box = nullptr, *d_thr = nullptr; uint32_t* d_cnt = nullptr;
+  std::vector<float> thr(3 * (nb + 1));
+  CdfParams p;
+  p.N = natoms; p.nb = nb;
+  for (int d = 0; d < 3; d++) {
+    const double* e = edges + d * (nb + 1);
+    for (int k = 0; k <= nb; k++) {
+      float f = (float)e[k];
+      if ((double)f < e[k]) f = nextafterf(f, INFINITY);
+      thr[d * (nb + 1) + k] = f;
+    }
+    float top = (float)e[nb];
+    if ((double)top > e[nb]) top = nextafterf(top, -INFINITY);
+    p.t_top[d] = top;
+    p.inv_d[d] = (float)(nb / (e[nb] - e[0]));
+  }
+  {
+    RCK(cudaSetDevice(device));
+    const size_t nb3 = (size_t)nb * nb * nb;
+    const size_t nposb = sizeof(float) * 3 * (size_t)natoms * nsamples, ncntb = sizeof(uint32_t) * nb3 * nsamples;
+    RCK(cudaMalloc(&d_thr, sizeof(float) * thr.size()));
+    RCK(cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * thr.size(), cudaMemcpyHostToDevice, st));
+    if (dev_ptrs) { d_pos = const_cast<float*>(pos); d_box = const_cast<float*>(box); d_cnt = counts; }
+    else {
+      RCK(cudaMalloc(&d_pos, nposb)); RCK(cudaMalloc(&d_box, sizeof(float) * nsamples)); RCK(cudaMalloc(&d_cnt, ncntb));
+      RCK(cudaMemcpyAsync(d_pos, pos, nposb, cudaMemcpyHostToDevice, st));
+      RCK(cudaMemcpyAsync(d_box, box, sizeof(float) * nsamples, cudaMemcpyHostToDevice, st));
+    }
+    RCK(cudaMemsetAsync(d_cnt, 0, ncntb, st));
+    int nsplit = 1;
+    if (nsamples < 2 * 148) nsplit = (int)((2 * 148 + nsamples - 1) / nsamples);
+    int a_chunk = (natoms + nsplit - 1) / nsplit;
+    if (a_chunk < 64) a_chunk = natoms < 64 ? natoms : 64;
+    if (a_chunk > 2048) a_chunk = 2048;
+    nsplit = (natoms + a_chunk - 1) / a_chunk;
+    p.a_chunk = a_chunk;
+    const size_t smem = sizeof(float) * (3 * (size_t)a_chunk + 3 * (nb + 1)) + sizeof(uint32_t) * nb3;
+    RCK(cudaFuncSetAttribute(k_cdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.thr = d_thr;
+    for (int64_t s0 = 0; s0 < nsamples; s0 += 65535) {
+      const int ns = (int)((nsamples - s0) < 65535 ? (nsamples - s0) : 65535);
+      CdfParams q = p;
+      q.pos = d_pos + 3 * (size_t)natoms * s0; q.box = d_box + s0; q.counts = d_cnt + nb3 * s0;
+      k_cdf<<<dim3(nsplit, ns), T, smem, st>>>(q);
+      RCK(cudaGetLastError());
+    }
+    if (!dev_ptrs) {
+      RCK(cudaMemcpyAsync(counts, d_cnt, ncntb, cudaMemcpyDeviceToHost, st));
+      RCK(cudaStreamSynchronize(st));
+    }
+  }
+done:
+  if (rc != NM_OK) cudaStreamSynchronize(st);
+  if (d_thr) { cudaStreamSynchronize(st); cudaFree(d_thr); }
+  if (!dev_ptrs) { if (d_pos) cudaFree(d_pos); if (d_box) cudaFree(d_box); if (d_cnt) cudaFree(d_cnt); }
+  return rc;
+}

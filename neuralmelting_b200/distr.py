@@ -5,7 +5,7 @@ Same flags (lammps_distr.py:18-47; the Dask/joblib/PBS ones are accepted and ign
 (<prefix>.natoms/.box/.pos.npy written by lammps_parse.py, :63-70), same outputs <prefix>.dni.npy,
 <prefix>.r.npy, <prefix>.rdf.npy (:336-338) with the same dtypes. The 27-image all-pairs float32 distance
 histogram of calculate_rdf (:123-135) runs in the CUDA kernel of csrc/nm_rdf.cu, bit-exact bin counts.
-The Cartesian density (calculate_cdf, :161-171, -cb) is the next row of the scope table and is not written yet.
+The Cartesian pair-vector density (calculate_cdf, :161-171, -cb) follows in the same way (<prefix>.dn/.rv/.cdf.npy, :368-370).
 """
 import argparse
 import os
@@ -72,6 +72,31 @@ def calculate_rdfs(natoms, box, pos, r, device=0, batch=4096, verbose=False):
     return out
 
 
+def cartesian_setup(natoms, box, cbins):
+    """the CDF part of calculate_spatial (lammps_distr.py:108-116): edges RV (3, CBINS+1) float64 centred on zero and
+    the ideal-gas voxel population DN. RV is built in float64 as under the numpy-1 rules the script was written for."""
+    nrho = np.divide(natoms, np.power(box, 3))
+    l = float(np.min(box))
+    rv = np.array([np.linspace(0, l, cbins + 1) for _ in range(3)], dtype=np.float64)
+    rv -= l / 2
+    drv = rv[0, 1] - rv[0, 0]
+    dn = nrho * drv ** 3
+    return rv, dn
+
+
+def calculate_cdfs(natoms, box, pos, rv, device=0, batch=1024, verbose=False):
+    """calculate_cdf for every sample (lammps_distr.py:216-234): float32 array (S, CB, CB, CB) = counts / natoms"""
+    ns, cb = natoms.size, rv.shape[1] - 1
+    out = np.empty((ns, cb, cb, cb), dtype=np.float32)
+    for s0 in range(0, ns, batch):
+        s1 = min(ns, s0 + batch)
+        counts = nm.cdf_counts(pos[s0:s1], box[s0:s1], rv, device=device)
+        out[s0:s1] = counts.astype(np.float32) / natoms[s0:s1, None, None, None].astype(np.float32)
+        if verbose:
+            print("cdf: %d / %d samples" % (s1, ns))
+    return out
+
+
 def run(args):
     prefix = os.path.join(os.getcwd(), "%s.%s.%s.lammps" % (args.name, args.element.lower(), LAT[args.element]))
     P = np.load(prefix + ".virial.trgt.npy")
@@ -92,8 +117,15 @@ def run(args):
     np.save(prefix + ".dni.npy", dni)
     np.save(prefix + ".r.npy", r)
     np.save(prefix + ".rdf.npy", g)
+    rv, dn = cartesian_setup(natoms, box, args.cartesian_bins)
+    c = calculate_cdfs(natoms, box, pos, rv, verbose=args.verbose)
+    c = np.divide(c, dn[:, np.newaxis, np.newaxis, np.newaxis])      # lammps_distr.py:365
+    c = c.reshape(pn, tn, rns, *(3 * (rv.shape[1] - 1,)))
+    np.save(prefix + ".dn.npy", dn)
+    np.save(prefix + ".rv.npy", rv)
+    np.save(prefix + ".cdf.npy", c)
     if args.verbose:
-        print("rdf written; the cartesian density (-cb) stage is not part of this build yet")
+        print("calculations finalized")
     return g
 
 

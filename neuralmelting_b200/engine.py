@@ -75,6 +75,8 @@ def load_library():
     L.nm_get_counters.argtypes = [C.c_void_p, C.c_void_p]
     L.nm_rdf_counts.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                 C.c_void_p, C.c_int32, C.c_void_p]
+    L.nm_cdf_counts.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                C.c_void_p, C.c_int32, C.c_void_p]
     L.nm_format_thrm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.nm_format_traj.argtypes = [C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
     L.nm_measure_fma_peak.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -261,6 +263,28 @@ def rdf_counts_device(pos_ptr, box_ptr, natoms, nsamples, edges, counts_ptr, dev
     edges = np.ascontiguousarray(edges, dtype=np.float64)
     _check(load_library().nm_rdf_counts(device, C.c_void_p(stream or 0), 1, C.c_void_p(pos_ptr), C.c_void_p(box_ptr),
                                         natoms, nsamples, _ptr(edges), edges.size, C.c_void_p(counts_ptr)))
+
+
+def cdf_counts(pos, box, edges, device=0, stream=None):
+    """calculate_cdf (lammps_distr.py:161-171) before '/natoms' for a batch of samples on the GPU.
+    pos (S,N,3) float32, box (S,) float32, edges (3, CBINS+1) float64 -> counts (S,CBINS,CBINS,CBINS) uint32"""
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    if pos.ndim == 2:
+        pos = pos[None]
+    ns, n = pos.shape[0], pos.shape[1]
+    box = np.ascontiguousarray(box, dtype=np.float32).reshape(-1)
+    if box.size != ns:
+        raise ValueError("box must have one entry per sample")
+    edges = np.ascontiguousarray(edges, dtype=np.float64)
+    if edges.ndim != 2 or edges.shape[0] != 3:
+        raise ValueError("edges must have shape (3, bins + 1)")
+    nb = edges.shape[1] - 1
+    counts = np.zeros((ns, nb, nb, nb), dtype=np.uint32)
+    if ns == 0:
+        return counts
+    _check(load_library().nm_cdf_counts(device, C.c_void_p(stream or 0), 0, _ptr(pos), _ptr(box), n, ns,
+                                        _ptr(edges), nb, _ptr(counts)))
+    return counts
 
 
 # ----------------------------------------------------------------------------- a-13 native text

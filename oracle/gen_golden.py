@@ -7,6 +7,7 @@ The GPU box has no /root/reference; tests read the committed fixtures instead.
 What is pinned here (reference = /root/reference/scripts):
   * calculate_rdf            lammps_distr.py:123-135   (numba njit, as shipped)
   * calculate_spatial edges  lammps_distr.py:82-98     (restated inline: R, DNI)
+  * calculate_cdf            lammps_distr.py:161-171   (.py_func: pure NumPy histogramdd)
   * replica_exchange         lammps_remcmc.py:776-803  (.py_func, module globals injected)
   * gen_mc_param             lammps_remcmc.py:726-745
   * write_thrm / write_traj / init_header  lammps_remcmc.py:176-256
@@ -75,6 +76,38 @@ def gen_rdf():
         cases[name] = dict(pos=pos, box=boxes, natoms=natoms, r=r, dni=dni, g=g)
     np.savez_compressed(os.path.join(OUT, "rdf_reference.npz"),
                         **{"%s_%s" % (k, f): v for k, d in cases.items() for f, v in d.items()})
+
+
+def gen_cdf():
+    """calculate_cdf.py_func (the jitted wrapper raises TypingError under numba 0.65: np.histogramdd unsupported)"""
+    sys.path.insert(0, REF)
+    import lammps_distr as ld
+    rng = np.random.default_rng(77)
+    out = {}
+    for name, sz, cb in (("n108_cb8", 3, 8), ("n256_cb11", 4, 11)):
+        n = 4 * sz ** 3
+        boxes = np.array([float("%.4E" % (sz * a)) for a in (1.56, 1.7)], dtype=np.float32)
+        pos = np.zeros((2, n, 3), dtype=np.float32)
+        for s in range(2):
+            x = fcc(sz, float(boxes[s])) + rng.normal(0, 0.2, (n, 3))
+            x -= np.floor(x / float(boxes[s])) * float(boxes[s])
+            if s == 1:
+                x[:4] += float(boxes[s])
+                x[0] = 0.0
+            pos[s] = text_roundtrip(x)
+        l = float(np.min(boxes))
+        rv = np.array([np.linspace(0, l, cb + 1) for _ in range(3)], dtype=np.float64)
+        rv -= l / 2
+        b = [-1, 0, 1]
+        br = np.array([[b[i], b[j], b[k]] for i in range(3) for j in range(3) for k in range(3)], dtype=np.int8)
+        cd = np.zeros((cb, cb, cb), dtype=np.float32)
+        res = []
+        for s in range(2):
+            res.append(np.array(ld.calculate_cdf.py_func(np.uint16(n), boxes[s], br, pos[s], rv, cd)))
+        res = np.array(res)
+        print("cdf", name, res.dtype, "counts", (res * n).sum(axis=(1, 2, 3)))
+        out.update({name + "_pos": pos, name + "_box": boxes, name + "_rv": rv, name + "_c": res, name + "_natoms": np.full(2, n, np.uint16)})
+    np.savez_compressed(os.path.join(OUT, "cdf_reference.npz"), **out)
 
 
 def import_remcmc():
@@ -205,6 +238,7 @@ def gen_adapt_and_text(lr):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_rdf()
+    gen_cdf()
     lr = import_remcmc()
     gen_exchange(lr)
     gen_adapt_and_text(lr)

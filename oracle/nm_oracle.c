@@ -578,6 +578,33 @@ ORC_API void orc_rdf_counts(int32_t n, const float* pos, float box, const double
   }
 }
 
+/* N1: calculate_cdf, lammps_distr.py:161-171, before the final '/natoms': for each of the 27 image vectors
+ * np.histogramdd of the float32 pair vectors on the float64 edges rv[3][nb+1] (searchsorted side='right', the
+ * right-most edge closed, outliers dropped). counts[nb][nb][nb]. */
+static int cdf_bin(float x, const double* e, int nb) {
+  const double v = (double)x;
+  if (!(v >= e[0] && v <= e[nb])) return -1;
+  int lo = 0, hi = nb;                        /* largest k with e[k] <= v */
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (v < e[mid]) hi = mid - 1; else lo = mid; }
+  return lo == nb ? nb - 1 : lo;
+}
+ORC_API void orc_cdf_counts(int32_t n, const float* pos, float box, const double* rv, int32_t nb, uint32_t* counts) {
+  memset(counts, 0, sizeof(uint32_t) * (size_t)nb * nb * nb);
+  static const int b[3] = {-1, 0, 1};
+  for (int i0 = 0; i0 < 3; i0++) for (int i1 = 0; i1 < 3; i1++) for (int i2 = 0; i2 < 3; i2++) {
+    float s[3] = { box * (float)b[i0], box * (float)b[i1], box * (float)b[i2] };
+    for (int q = 0; q < n; q++) {
+      float img[3] = { pos[3 * q] + s[0], pos[3 * q + 1] + s[1], pos[3 * q + 2] + s[2] };
+      for (int a = 0; a < n; a++) {
+        int bx = cdf_bin(pos[3 * a] - img[0], rv, nb); if (bx < 0) continue;
+        int by = cdf_bin(pos[3 * a + 1] - img[1], rv + (nb + 1), nb); if (by < 0) continue;
+        int bz = cdf_bin(pos[3 * a + 2] - img[2], rv + 2 * (nb + 1), nb); if (bz < 0) continue;
+        counts[((size_t)bx * nb + by) * nb + bz]++;
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ replica farm (CPU baseline) */
 typedef struct {
   const orc_params* p; const double* labels; int32_t slot0, nrep, n; int64_t cycle0, ncycles;

@@ -272,3 +272,39 @@ def rdf_counts_numpy(pos, box, r):
         d = np.sqrt((sq[..., 0] + sq[..., 1]) + sq[..., 2])
         rd[1:] += np.histogram(d, r)[0]
     return rd.astype(np.uint32)
+
+
+# ----------------------------------------------------------------------------- CDF (next row N1)
+def cdf_edges(box_all, cbins):
+    """RV of calculate_spatial (lammps_distr.py:109-111): three rows of CBINS+1 float64 edges centred on 0
+    (float64 as under the numpy-1 rules the script was written for)"""
+    l = float(np.min(box_all))
+    rv = np.array([np.linspace(0, l, cbins + 1) for _ in range(3)], dtype=np.float64)
+    rv -= l / 2
+    return rv
+
+
+def cdf_counts(pos, box, rv):
+    """C restatement of calculate_cdf before '/natoms' (lammps_distr.py:161-170)"""
+    pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+    rv = np.ascontiguousarray(rv, dtype=np.float64)
+    nb = rv.shape[1] - 1
+    counts = np.zeros((nb, nb, nb), dtype=np.uint32)
+    lib().orc_cdf_counts(C.c_int32(pos.shape[0]), pos.ctypes.data_as(C.POINTER(C.c_float)), C.c_float(np.float32(box)),
+                         _dp(rv), C.c_int32(nb), counts.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return counts
+
+
+def cdf_counts_numpy(pos, box, rv):
+    """NumPy restatement: np.histogramdd per image on the float32 pair vectors"""
+    pos = np.asarray(pos, dtype=np.float32).reshape(-1, 3)
+    box = np.float32(box)
+    b = [-1, 0, 1]
+    br = np.array([[b[i], b[j], b[k]] for i in range(3) for j in range(3) for k in range(3)], dtype=np.int8)
+    nb = rv.shape[1] - 1
+    cd = np.zeros((nb, nb, nb), dtype=np.float32)
+    for j in range(br.shape[0]):
+        shift = (box * br[j].astype(np.float32)).astype(np.float32)
+        dvm = pos - (pos + shift.reshape(1, -1)).reshape(-1, 1, 3)
+        cd += np.histogramdd(dvm.reshape(-1, 3), list(rv))[0]
+    return cd.astype(np.uint32)

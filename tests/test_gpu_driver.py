@@ -52,7 +52,10 @@ def test_remcmc_run_writes_reference_compatible_files(nm, orc, tmp_path):
         np.save(pref + ".natoms.npy", natoms)
         np.save(pref + ".box.npy", box)
         np.save(pref + ".pos.npy", x)
-        g = distr.run(distr.build_parser().parse_args("-n t1 -sb 32".split()))
+        g = distr.run(distr.build_parser().parse_args("-n t1 -sb 32 -cb 6".split()))
+        cdf = np.load(pref + ".cdf.npy")
+        assert cdf.shape == (2, 3, 3, 6, 6, 6) and np.load(pref + ".rv.npy").shape == (3, 7) and np.load(pref + ".dn.npy").shape == (18,)
+        assert abs(cdf.mean() - 1.0) < 0.35          # pair density relative to the ideal gas, averaged over the cell
         assert g.shape == (2, 3, 3, 32) and g.dtype == np.float64
         r = np.load(pref + ".r.npy")
         flat_x, flat_n = x.reshape(-1, 256, 3), natoms.reshape(-1)

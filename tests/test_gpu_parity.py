@@ -369,7 +369,7 @@ def test_ensemble_averages_agree_with_oracle(nm, orc):
 @pytest.mark.parametrize("n_side", [4, 5, 10])
 def test_fp32_mode_eval_within_1e5(nm, orc, n_side):
     rho = [1.122, 1.1, 0.9, 0.6]
-    sig = [0.0, 0.05, 0.10, 0.12]            # physical configurations (no near-overlaps: r^-13 amplifies float32 positions)
+    sig = [0.0, 0.05, 0.08, 0.08]            # physical configurations (no near-overlaps: r^-13 amplifies float32 positions)
     x, box = _configs(orc, n_side, rho, sig, seed=50 + n_side)
     n = 4 * n_side ** 3
     with nm.Engine(natoms=n, n_rep=len(box), nt=len(box), precision=32) as eng:
@@ -399,3 +399,27 @@ def test_fp32_mode_cycle_tracks_fp64(nm, orc):
             out[prec] = eng.get_thermo()
     np.testing.assert_array_equal(out[32][:, 9:15], out[64][:, 9:15])
     np.testing.assert_allclose(out[32][:, :6], out[64][:, :6], rtol=2e-4)
+
+
+# ------------------------------------------------------------------ N1: Cartesian pair-vector density
+@pytest.mark.parametrize("name", ["n108_cb8", "n256_cb11"])
+def test_cdf_matches_reference_golden(nm, orc, name):
+    g = np.load(os.path.join(GOLDEN, "cdf_reference.npz"))
+    pos, box, rv, ref, nat = (g["%s_%s" % (name, f)] for f in ("pos", "box", "rv", "c", "natoms"))
+    counts = nm.cdf_counts(pos, box, rv)
+    assert counts.dtype == np.uint32 and counts.shape == ref.shape
+    np.testing.assert_array_equal(counts.astype(np.float32) / nat[:, None, None, None].astype(np.float32), ref)
+
+
+def test_cdf_edge_cases(nm, orc):
+    rng = np.random.default_rng(4)
+    for n, cb in ((1, 3), (2, 16), (70, 5), (300, 11), (300, 32)):
+        box = np.array([4.0, 4.6], dtype=np.float32)
+        pos = (rng.uniform(-0.1, 1.1, (2, n, 3)) * box[:, None, None]).astype(np.float32)
+        pos[0, 0] = 0.0
+        rv = orc.cdf_edges(box, cb)
+        got = nm.cdf_counts(pos, box, rv)
+        for s in range(2):
+            np.testing.assert_array_equal(got[s], orc.cdf_counts(pos[s], box[s], rv))
+    with pytest.raises(nm.NmError):
+        nm.cdf_counts(pos, box, orc.cdf_edges(box, 33))

@@ -45,3 +45,16 @@ def test_round6_is_the_text_round_trip(orc):
     rng = np.random.default_rng(0)
     for v in list(rng.uniform(0, 20, 200)) + [0.0350625, 0.00390625, 6.1105790881, 1e-7, 123456.7890125]:
         assert orc.lib().orc_round6(v) == float("%f" % v)
+
+
+@pytest.mark.parametrize("name", ["n108_cb8", "n256_cb11"])
+def test_cdf_oracle_matches_reference(orc, name):
+    """N1: calculate_cdf.py_func run in the build container (np.histogramdd per image, float32 vectors, float64 edges)"""
+    g = np.load(os.path.join(GOLDEN, "cdf_reference.npz"))
+    pos, box, rv, ref, nat = (g["%s_%s" % (name, f)] for f in ("pos", "box", "rv", "c", "natoms"))
+    assert rv.dtype == np.float64 and ref.dtype == np.float32
+    np.testing.assert_array_equal(orc.cdf_edges(box, rv.shape[1] - 1), rv)
+    for s in range(pos.shape[0]):
+        c = orc.cdf_counts(pos[s], box[s], rv)
+        np.testing.assert_array_equal(c.astype(np.float32) / np.float32(nat[s]), ref[s])
+    np.testing.assert_array_equal(orc.cdf_counts_numpy(pos[0], box[0], rv), orc.cdf_counts(pos[0], box[0], rv))
