@@ -46,9 +46,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--rdf-samples", type=int, default=1024, help="c5: samples per step (N = 4000, SBINS = 64)")
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    ap.add_argument("--equil", type=int, default=4, help="untimed equilibration cycles before the warm-up")
+    ap.add_argument("--equil", type=int, default=8, help="untimed equilibration cycles before the warm-up")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="pair arithmetic: 64 (headline) or the FP32 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
@@ -345,8 +346,94 @@ def run_reference(args):
             "note": "CPU restatement of lammps_remcmc.py's per-replica path (LAMMPS + Dask are not installable here); one replica per task over all host threads"}
 
 
+def run_rdf(args):
+    """c5 (BASELINE configs[4]): RDF feature extraction (lammps_distr.py:123-135) over samples of 4000-atom configurations.
+    A step = one batch of --rdf-samples samples; value = samples/s with the positions resident in HBM; e2e = from host
+    arrays through nm_rdf_counts (H2D of positions, D2H of counts inside the timed region). HBM roofline: 12 N + 6 bytes
+    in, 4 SBINS out per sample -- the kernel is FP32-ALU bound, the fraction is reported for the record."""
+    import torch
+    from neuralmelting_b200 import engine as nm
+    from neuralmelting_b200 import remcmc
+    comm = remcmc.Comm()
+    dev = comm.local_rank
+    torch.cuda.set_device(dev)
+    n, sb, ns = 4000, 64, args.rdf_samples
+    rng = np.random.default_rng(5 + comm.rank)
+    box = rng.uniform(15.2, 20.5, ns).astype(np.float32)                 # the density range of the 32x32 grid
+    pos = (rng.uniform(0, 1, (ns, n, 3)) * box[:, None, None]).astype(np.float32)
+    l = np.float32(15.2)
+    r = np.linspace(1e-16, 1 / 2, sb) * l
+    d_pos = torch.from_numpy(pos).cuda(); d_box = torch.from_numpy(box).cuda()
+    d_cnt = torch.zeros((ns, sb), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        nm.rdf_counts_device(d_pos.data_ptr(), d_box.data_ptr(), n, ns, r, d_cnt.data_ptr(), device=dev, stream=stream)
+    sampler = ClockSampler(dev) if comm.rank == 0 else None
+    for _ in range(max(12, args.warmup)):          # short steps: warm up for ~0.5 s so that the SM clock has ramped
+        step()
+    comm.barrier(); torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    comm.barrier(); torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    ms = t0.elapsed_time(t1)
+    w0 = time.perf_counter()
+    e2e_steps = 2
+    for _ in range(e2e_steps):
+        got = nm.rdf_counts(pos, box, r, device=dev)
+    e2e_s = time.perf_counter() - w0
+    vals = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if comm.world > 1:
+        comm.dist.all_reduce(vals, op=comm.dist.ReduceOp.MAX)
+    ms, e2e_ms = (float(t) for t in vals.cpu())
+    if comm.rank != 0:
+        return None
+    bytes_per_sample = 12 * n + 6 + 4 * sb
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_per_sample * ns * args.steps * comm.world / (ms * 1e-3) / 1e9 / comm.world
+    out = {"metric": "rdf_samples_per_sec", "value": ns * args.steps * comm.world / (ms * 1e-3), "unit": "samples/s",
+           "n_gpus": comm.world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic: uniform random positions of 4000 atoms, boxes 15.2-20.5 (the density range of the 32x32 grid)",
+           "config": {"workload": "C5: RDF histogram (lammps_distr.calculate_rdf), N=4000, SBINS=64, %d samples per step per GPU" % ns,
+                      "l2": "inputs %.0f MB per step %s L2" % (12e-6 * n * ns, "larger than" if 12 * n * ns > 126e6 else "fit in; compute-bound kernel")},
+           "ordered_pair_distances_per_sec": n * (n - 1.0) * ns * args.steps * comm.world / (ms * 1e-3),
+           "e2e": {"value": ns * e2e_steps * comm.world / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": (12 * n + 4) * ns,
+                   "d2h_bytes_per_step": 4 * sb * ns, "steps": e2e_steps},
+           "gpu_launches": args.steps * comm.world,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "nmrdf::k_rdf", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                        "note": "algorithmic bytes %d per sample; the kernel is bound by FP32/integer issue (N(N-1) ordered pair distances per sample), not by HBM" % bytes_per_sample},
+           "clocks": clocks}
+    if comm.world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        nsamp = max(cores, 2)
+        t0c = time.perf_counter()
+        ref = orc.rdf_counts_farm(pos[:nsamp], box[:nsamp], r, nthreads=cores)
+        tc = time.perf_counter() - t0c
+        assert np.array_equal(ref, got[:nsamp]), "rdf parity"
+        out["cpu_baseline"] = {"value": nsamp / tc, "unit": "samples/s", "cores": cores, "kind": "port", "seconds": tc,
+                               "sample": "%d samples of the same batch, one per thread (27-image all-pairs float32 loop of the reference, in C)" % nsamp}
+    return out
+
+
 def main():
     args = parse()
+    if args.workload == "c5":
+        out = run_rdf(args) if args.impl != "reference" else None
+        if out is not None:
+            print(json.dumps(out))
+        return
     out = run_reference(args) if args.impl == "reference" else run_b200(args)
     if out is not None:
         print(json.dumps(out))

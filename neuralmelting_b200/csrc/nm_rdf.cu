@@ -40,7 +40,7 @@ __device__ __forceinline__ void count_one(float dx, float dy, float dz, const Rd
     while (k > 0 && d < sthr[k]) k--;
     while (k < p.nb - 1 && d >= sthr[k + 1]) k++;
     if (k == p.nb - 1) k = p.nb - 2;                       // last bin is right-closed
-    if (p.private_hist) hist[k * T + threadIdx.x]++;
+    if (p.private_hist) reinterpret_cast<unsigned short*>(hist)[k * T + threadIdx.x]++;
     else atomicAdd(&hist[k], 1u);
   }
 }
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(T) k_rdf(RdfParams p) {
   const float* ps = p.pos + (size_t)s * p.N * 3;
   for (int a = threadIdx.x; a < na; a += T) { ax[a] = ps[3 * (a0 + a)]; ay[a] = ps[3 * (a0 + a) + 1]; az[a] = ps[3 * (a0 + a) + 2]; }
   for (int k = threadIdx.x; k < p.nb; k += T) sthr[k] = p.thr[k];
-  const int nh = p.private_hist ? p.nb * T : p.nb;
+  const int nh = p.private_hist ? p.nb * T / 2 : p.nb;     // private columns are 16-bit (two per word)
   for (int k = threadIdx.x; k < nh; k += T) hist[k] = 0u;
   __syncthreads();
   const float bx = p.box[s], nbx = __fmul_rn(bx, -1.0f), cut = p.cut;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(T) k_rdf(RdfParams p) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int k = wid; k < p.nb - 1; k += T / 32) {
       uint32_t v = 0;
-      for (int j = lane; j < T; j += 32) v += hist[k * T + j];
+      for (int j = lane; j < T; j += 32) v += reinterpret_cast<unsigned short*>(hist)[k * T + j];
       v = __reduce_add_sync(0xffffffffu, v);
       if (lane == 0 && v) atomicAdd(&out[1 + k], v);
     }
@@ -154,12 +154,14 @@ extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
     if (nsamples < 2 * 148) nsplit = (int)((2 * 148 + nsamples - 1) / nsamples);
     int a_chunk = (natoms + nsplit - 1) / nsplit;
     if (a_chunk < 64) a_chunk = natoms < 64 ? natoms : 64;
-    if (a_chunk > 2048) a_chunk = 2048;      // 24 KB of positions + the private histogram: two CTAs per SM
+    if (a_chunk > 1024) a_chunk = 1024;      // 12 KB of positions + 32 KB of 16-bit private histogram columns: five CTAs per SM
+    // a thread counts at most a_chunk * ceil(natoms / T) pairs: keep that inside 16 bits
+    { const int per_thread = (natoms + T - 1) / T; if ((long long)a_chunk * per_thread > 65535) a_chunk = 65535 / per_thread; if (a_chunk < 1) a_chunk = 1; }
     nsplit = (natoms + a_chunk - 1) / a_chunk;
     p.a_chunk = a_chunk;
     const size_t base = sizeof(float) * (3 * (size_t)a_chunk + nbins);
-    p.private_hist = (base + sizeof(uint32_t) * (size_t)nbins * T) <= 200 * 1024;
-    const size_t smem = base + sizeof(uint32_t) * (size_t)nbins * (p.private_hist ? T : 1);
+    p.private_hist = (base + sizeof(unsigned short) * (size_t)nbins * T) <= 200 * 1024 && (nbins * T) % 2 == 0;
+    const size_t smem = base + (p.private_hist ? sizeof(unsigned short) * (size_t)nbins * T : sizeof(uint32_t) * (size_t)nbins);
     RCK(cudaFuncSetAttribute(k_rdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.pos = d_pos; p.box = d_box; p.counts = d_cnt; p.thr = d_thr;
     for (int64_t s0 = 0; s0 < nsamples; s0 += 65535) {       // gridDim.y limit
