@@ -423,3 +423,26 @@ def test_cdf_edge_cases(nm, orc):
             np.testing.assert_array_equal(got[s], orc.cdf_counts(pos[s], box[s], rv))
     with pytest.raises(nm.NmError):
         nm.cdf_counts(pos, box, orc.cdf_edges(box, 33))
+
+
+# ------------------------------------------------------------------ small boxes: per-pair minimum-image path
+def test_small_box_minimum_image_path(nm, orc):
+    """box < 2 (rc + skin): image codes are not stable between builds, the kernel resolves the image per pair (MIC path)"""
+    x, box = _configs(orc, 4, [1.17, 1.12], [0.04, 0.06], seed=71)       # L = 6.03, 6.11 < 2 * (2.5 + 0.6)
+    box = np.array([orc.round6(b) for b in box])
+    with nm.Engine(natoms=256, n_rep=2, nt=2, skin=0.6, mod=16, bulk_move=True, seed=5) as eng:
+        eng.set_labels([0.5, 1.0], [8.0, 4.0], [0.5, 1.0])
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[.03, .03], dv=[.03, .03], dt=[.004, .004])
+        pe, w, f, npairs = eng.eval()
+        for k in range(2):
+            pe_o, w_o, f_o, np_o = orc.lj_eval_list(x[k], box[k])
+            assert npairs[k] == np_o and abs(pe[k] - pe_o) <= 1e-10 * abs(pe_o)
+            assert np.abs(f[k] - f_o).max() <= 1e-10 * np.abs(f_o).max()
+        eng.run_cycle(0)
+        th = eng.get_thermo()
+    params = orc.make_params(mod=16, bulk_move=1, seed=5)
+    for k, (T, P) in enumerate(((0.5, 4.0), (1.0, 4.0))):
+        xo, vo = x[k].copy(), np.zeros(768)
+        th_o, _ = orc.cycle(params, [T, P / T, T, orc.round6(T)], k, 0, xo, vo, np.array([box[k], .03, .03, .004]), np.zeros(6))
+        np.testing.assert_array_equal(th[k, 9:], th_o[9:])
+        np.testing.assert_allclose(th[k, :9], th_o[:9], rtol=2e-9, atol=1e-9)
