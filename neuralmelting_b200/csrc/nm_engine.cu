@@ -246,13 +246,11 @@ __device__ int grouped_rows(const Dev& d, Ctx& cx, float rl2f, int nc) {
     }
     if (cnt > d.maxnbo) { over = 1; cnt = d.maxnbo; }
     if (!BITS && (cnt & 3)) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
-    ushort4* orow = cx.olist + (size_t)i * d.maxqo;
-    uint8_t* crow = cx.ocode + (size_t)i * d.maxqo;
     const int sx = pi.x < 0.5f ? -1 : 1, sy = pi.y < 0.5f ? -1 : 1, sz = pi.z < 0.5f ? -1 : 1;
     int q = 0;
     auto emit = [&](ushort4 v, int code) {
       if (BITS) cx.list[(size_t)q * Npad + i] = pack_code(v, code);
-      else { orow[q] = v; crow[q] = (uint8_t)code; }
+      else { cx.olist[(size_t)q * Npad + i] = v; cx.ocode[(size_t)q * Npad + i] = (uint8_t)code; }
       q++;
     };
     for (int g = 0; g < 8; g++) {
@@ -530,7 +528,9 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
 }
 
 // inner list = the outer entries currently within rl (float32 test with the stored image; minimum image in MIC mode).
-// The owning thread streams its outer row and emits whole 8-byte quads into the [quad][atom] layout the force loop reads.
+// The owning thread streams its outer row (already ordered by image group, so the inner row inherits the grouping),
+// packs the surviving indices four at a time into one 64-bit register (stored XOR the dummy index, so that untouched
+// fields read as the dummy atom) and emits whole 8-byte quads into the [quad][atom] layout the force loop reads.
 __device__ void build_inner(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
@@ -540,26 +540,30 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
   const float magic = 12582912.f;
   const bool mic = cx.mic;
+  const unsigned long long dummy4 = 0x0001000100010001ull * (unsigned long long)N;
+  unsigned long long* l64 = reinterpret_cast<unsigned long long*>(cx.list);
   double tot = 0.0; int over = 0;
   for (int i = tid; i < N; i += nthr) {
     const float4 pi = cx.sf[i];
     const int nqo = cx.onq[i];
-    const ushort4* orow = cx.olist + (size_t)i * d.maxqo;
-    const uint8_t* crow = cx.ocode + (size_t)i * d.maxqo;
-    unsigned short a0 = (unsigned short)N, a1 = a0, a2 = a0, a3 = a0;
+    const ushort4* orow = cx.olist + i;          // [quad][atom]: a warp reads 256 contiguous bytes per quad
+    const uint8_t* crow = cx.ocode + i;
+    unsigned long long acc = 0ull;
     int oq = 0, fill = 0, curcode = 13, cnt = 0;
     auto flush = [&]() {
-      if (oq < d.maxq) cx.list[(size_t)oq * Npad + i] = pack_code(make_ushort4(a0, a1, a2, a3), curcode);
-      else over = 1;
-      oq++; fill = 0; a0 = a1 = a2 = a3 = (unsigned short)N;
+      if (oq < d.maxq) {
+        const unsigned long long codebits = ((unsigned long long)(curcode & 7) << 13) | ((unsigned long long)(curcode >> 3) << 29);
+        l64[(size_t)oq * Npad + i] = (acc ^ dummy4) | codebits;
+      } else over = 1;
+      oq++; fill = 0; acc = 0ull;
     };
     ushort4 e4 = nqo > 0 ? orow[0] : make_ushort4(0, 0, 0, 0);
     int code = nqo > 0 ? crow[0] : 13;
     for (int q = 0; q < nqo; q++) {
-      const ushort4 n4 = (q + 1 < nqo) ? orow[q + 1] : e4;
-      const int ncode = (q + 1 < nqo) ? crow[q + 1] : 13;
-      const float sx = (float)(code / 9 - 1), sy = (float)((code / 3) % 3 - 1), sz = (float)(code % 3 - 1);
+      const ushort4 n4 = (q + 1 < nqo) ? orow[(size_t)(q + 1) * Npad] : e4;
+      const int ncode = (q + 1 < nqo) ? crow[(size_t)(q + 1) * Npad] : 13;
       if (code != curcode) { if (fill) flush(); curcode = code; }
+      const float sx = (float)(code / 9 - 1), sy = (float)((code / 3) % 3 - 1), sz = (float)(code % 3 - 1);
       const int jj[4] = { e4.x, e4.y, e4.z, e4.w };
 #pragma unroll
       for (int t = 0; t < 4; t++) {
@@ -569,8 +573,7 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
         else { dx -= sx; dy -= sy; dz -= sz; }
         const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         if (r2 < rl2f) {
-          const unsigned short j = (unsigned short)jj[t];
-          a0 = fill == 0 ? j : a0; a1 = fill == 1 ? j : a1; a2 = fill == 2 ? j : a2; a3 = fill == 3 ? j : a3;
+          acc |= (unsigned long long)(jj[t] ^ N) << (16 * fill);
           cnt++;
           if (++fill == 4) flush();
         }
@@ -1415,7 +1418,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   d.nstps = cfg->nstps; d.mod = cfg->mod; d.bulk = cfg->bulk_move; d.text_rounding = cfg->text_rounding;
   d.ppos = cfg->ppos; d.pvol = cfg->pvol; d.lat = cfg->lat_scale; d.mass = cfg->mass; d.rc = cfg->rc;
   d.skin = cfg->skin > 0 ? cfg->skin : 0.3;
-  d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 0.8;
+  d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 1.0;
   d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);
   {
     // list capacities: neighbours inside the list radius at the densest state we expect (rho* 1.6) plus slack,
