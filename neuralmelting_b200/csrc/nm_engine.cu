@@ -20,7 +20,7 @@
 
 namespace nm {
 
-constexpr int NCMAX = 8;                 // cell grid is at most 8^3
+constexpr int NCMAX = 12;                // cell grid is at most 12^3
 constexpr int RED_DOUBLES = 32 * 12 + 12;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
@@ -192,7 +192,7 @@ __device__ __forceinline__ ushort4 pack_code(ushort4 v, int code) {
 // Candidates: all atoms (nc == 1), the 27 stencil cells (nc >= 3), or -- BITS -- the set bits of the atom's row in the
 // shared-memory hit matrix. Output: OUTER rows (row-major per atom) or, BITS mode, the [quad][atom] force-loop layout.
 template <bool BITS>
-__device__ int grouped_rows(const Dev& d, Ctx& cx, float rl2f, int nc) {
+__device__ int grouped_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double invL = 1.0 / cx.L;
   const float magic = 12582912.f;          // 1.5 * 2^23: (x + magic) - magic = rint(x) for |x| < 2^22
@@ -238,7 +238,7 @@ __device__ int grouped_rows(const Dev& d, Ctx& cx, float rl2f, int nc) {
       for (int j = 0; j < N; j++) test(j);
     } else {
       const int ci = cx.atom_cell[i], a = ci / (nc * nc), b = (ci / nc) % nc, e = ci % nc;
-      for (int da = -1; da <= 1; da++) for (int db = -1; db <= 1; db++) for (int de = -1; de <= 1; de++) {
+      for (int da = -sw; da <= sw; da++) for (int db = -sw; db <= sw; db++) for (int de = -sw; de <= sw; de++) {
         const int cc = (((a + da + nc) % nc) * nc + (b + db + nc) % nc) * nc + (e + de + nc) % nc;
         const int s = cx.cell_start[cc], en = cx.cell_start[cc + 1];
         for (int p = s; p < en; p++) test(cx.cell_atoms[p]);
@@ -471,9 +471,11 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
 __device__ void build_outer(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double L = cx.L, rlo = d.rc + d.skin + d.oskin, invL = 1.0 / L;
-  int nc = (int)floor(L / (rlo * (1.0 + 1e-4)));
+  // cells of side >= rlo/2 searched with a 5^3 stencil when the box allows it (fewer candidates per atom than
+  // cells of side >= rlo with a 3^3 stencil); all atoms when the box is below 3 rlo
+  int sw = 2, nc = (int)floor(2.0 * L / (rlo * (1.0 + 1e-4)));
   if (nc > NCMAX) nc = NCMAX;
-  if (nc < 3) nc = 1;
+  if (nc < 5) { sw = 1; nc = (int)floor(L / (rlo * (1.0 + 1e-4))); if (nc < 3) nc = 1; }
   const int ncell = nc * nc * nc;
   cx.mic = L < 2.0 * rlo * (1.0 + 1e-3);    // small box: the nearest image of a listed pair may change between builds
   __syncthreads();
@@ -520,7 +522,7 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
     __syncthreads();
   }
   const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
-  const int over = grouped_rows<false>(d, cx, rl2f, nc);
+  const int over = grouped_rows<false>(d, cx, rl2f, nc, sw);
   if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
   cx.L0o = L;
   update_thr(d, cx);
