@@ -79,8 +79,10 @@ class ClockSampler:
     def __init__(self, device):
         self.proc = None
         self.device = device
+        if os.environ.get("NM_BENCH_NO_SAMPLER"):
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", os.environ.get("NM_BENCH_SAMPLER_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
