@@ -1058,11 +1058,29 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
       double umax = um[0];
       const double s = L / cx.L0;
       int kk = k, need = 0;
+      // software pipeline: the list column, quad count and list reference of the NEXT atom are fetched from global
+      // memory while the current trial is evaluated (one warp walks the sequential chain; latency is everything)
+      int nq_n = cx.nnb[kk];
+      ushort4 e4_n = lane < nq_n ? cx.list[(size_t)lane * Npad + kk] : make_ushort4(0, 0, 0, 0);
+      double x0_n = lane < 3 ? cx.gx0[lane * Npad + kk] : 0.0;
       for (; kk < N; kk++) {
+        const int nq = nq_n; const ushort4 e4c = e4_n; const double x0c = x0_n;
+        if (kk + 1 < N) {
+          nq_n = cx.nnb[kk + 1];
+          e4_n = lane < nq_n ? cx.list[(size_t)lane * Npad + kk + 1] : make_ushort4(0, 0, 0, 0);
+          x0_n = lane < 3 ? cx.gx0[lane * Npad + kk + 1] : 0.0;
+        }
         double u[3]; rng_uniform3(r, (uint32_t)kk, P_ITER_DISP, u);
-        const double xo = cx.sp[3 * (kk)], yo = cx.sp[3 * (kk) + 1], zo = cx.sp[3 * (kk) + 2];
+        const double uacc = rng_uniform(r, (uint32_t)kk, P_ITER_ACC);       // independent of the energy: off the critical path
+        const double xo = cx.sp[3 * kk], yo = cx.sp[3 * kk + 1], zo = cx.sp[3 * kk + 2];
         double xn = xo + 2 * (u[0] - 0.5) * dxs * d.lat, yn = yo + 2 * (u[1] - 0.5) * dxs * d.lat, zn = zo + 2 * (u[2] - 0.5) * dxs * d.lat;
-        const double un = sqrt(disp2(cx, kk, xn, yn, zn, invL));
+        double un;
+        {
+          const double rx = __shfl_sync(0xffffffffu, x0c, 0), ry = __shfl_sync(0xffffffffu, x0c, 1), rz = __shfl_sync(0xffffffffu, x0c, 2);
+          double ux = xn * invL - rx, uy = yn * invL - ry, uz = zn * invL - rz;
+          ux -= rint(ux); uy -= rint(uy); uz -= rint(uz);
+          un = sqrt(ux * ux + uy * uy + uz * uz) * cx.L0;
+        }
         // every atom within rc of the old or the new position must be in column kk of the list
         const bool list_ok = s * (rl - un - umax) >= rc * (1 + 1e-9) && s * (rl - 2.0 * umax) >= rc * (1 + 1e-9);
         bool brute = false;
@@ -1074,28 +1092,31 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
         }
         double de = 0.0; int vis = 0;
         auto pair = [&](int j) {
-          const double ax = mic_exact(xn - cx.sp[3 * (j)], L, hL), ay = mic_exact(yn - cx.sp[3 * (j) + 1], L, hL), az = mic_exact(zn - cx.sp[3 * (j) + 2], L, hL);
-          const double bx = mic_exact(xo - cx.sp[3 * (j)], L, hL), by = mic_exact(yo - cx.sp[3 * (j) + 1], L, hL), bz = mic_exact(zo - cx.sp[3 * (j) + 2], L, hL);
+          const double ax = mic_exact(xn - cx.sp[3 * j], L, hL), ay = mic_exact(yn - cx.sp[3 * j + 1], L, hL), az = mic_exact(zn - cx.sp[3 * j + 2], L, hL);
+          const double bx = mic_exact(xo - cx.sp[3 * j], L, hL), by = mic_exact(yo - cx.sp[3 * j + 1], L, hL), bz = mic_exact(zo - cx.sp[3 * j + 2], L, hL);
           const double rn = ax * ax + ay * ay + az * az, ro = bx * bx + by * by + bz * bz;
-          if (rn < rc2) { const double r2 = 1.0 / rn, r6 = r2 * r2 * r2; de += r6 * (4.0 * r6 - 4.0); vis++; }
-          if (ro < rc2) { const double r2 = 1.0 / ro, r6 = r2 * r2 * r2; de -= r6 * (4.0 * r6 - 4.0); vis++; }
+          const double r2n = rcp_nr(rn), r2o = rcp_nr(ro);
+          const double r6n = r2n * r2n * r2n, r6o = r2o * r2o * r2o;
+          if (rn < rc2) { de += r6n * (4.0 * r6n - 4.0); vis++; }
+          if (ro < rc2) { de -= r6o * (4.0 * r6o - 4.0); vis++; }
         };
         if (brute) {
           for (int j = lane; j < N; j += 32) if (j != kk) pair(j);
         } else {
-          const int nq = cx.nnb[kk];
-          for (int q = lane; q < nq; q += 32) {
+          if (lane < nq) { pair(e4c.x & 0x1fff); pair(e4c.y & 0x1fff); pair(e4c.z); pair(e4c.w); }
+          for (int q = lane + 32; q < nq; q += 32) {
             const ushort4 e4 = cx.list[(size_t)q * Npad + kk];
             pair(e4.x & 0x1fff); pair(e4.y & 0x1fff); pair(e4.z); pair(e4.w);
           }
         }
         for (int o = 16; o > 0; o >>= 1) { de += __shfl_xor_sync(0xffffffffu, de, o); vis += __shfl_xor_sync(0xffffffffu, vis, o); }
-        const bool acc = metropolis(de / et, r, (uint32_t)kk, P_ITER_ACC);
+        bool acc;
+        { const double m = exp(-(de / et)); acc = !(isinf(m) || isnan(m)) && uacc <= (m < 1.0 ? m : 1.0); }
         ntrial++; nvis += vis;
         if (acc) {
           nacc++; en.pe += de;
           __syncwarp();
-          if (lane == 0) { cx.sp[3 * (kk)] = xn; cx.sp[3 * (kk) + 1] = yn; cx.sp[3 * (kk) + 2] = zn; }
+          if (lane == 0) { cx.sp[3 * kk] = xn; cx.sp[3 * kk + 1] = yn; cx.sp[3 * kk + 2] = zn; }
           __syncwarp();
           umax = fmax(umax, un);
         }
