@@ -446,3 +446,44 @@ def test_small_box_minimum_image_path(nm, orc):
         th_o, _ = orc.cycle(params, [T, P / T, T, orc.round6(T)], k, 0, xo, vo, np.array([box[k], .03, .03, .004]), np.zeros(6))
         np.testing.assert_array_equal(th[k, 9:], th_o[9:])
         np.testing.assert_allclose(th[k, :9], th_o[:9], rtol=2e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------ size-independent properties at the BASELINE sizes
+@pytest.mark.parametrize("n_side", [5, 10])
+def test_eval_invariances_at_full_size(nm, orc, n_side):
+    """translation by an arbitrary vector (re-wrapped) and a permutation of the atom ids leave energy, virial and the
+    pair count unchanged and permute the forces; sum of forces vanishes (N = 500 and N = 4000)"""
+    rng = np.random.default_rng(n_side)
+    n = 4 * n_side ** 3
+    x, box = _configs(orc, n_side, [0.95], [0.12], seed=80 + n_side)
+    x0 = x[0].reshape(n, 3)
+    shift = rng.uniform(-3 * box[0], 3 * box[0], 3)
+    perm = rng.permutation(n)
+    xs = np.stack([x0, x0 + shift, x0[perm]]).reshape(3, -1)
+    with nm.Engine(natoms=n, n_rep=3, nt=3) as eng:
+        eng.set_state(x=xs, box=np.repeat(box, 3))
+        pe, w, f, npairs = eng.eval()
+    assert npairs[0] == npairs[1] == npairs[2]
+    assert abs(pe[1] - pe[0]) <= 1e-10 * abs(pe[0]) and abs(pe[2] - pe[0]) <= 1e-10 * abs(pe[0])
+    assert abs(w[1] - w[0]) <= 1e-10 * abs(w[0]) and abs(w[2] - w[0]) <= 1e-10 * abs(w[0])
+    fs = np.abs(f[0]).max()
+    assert np.abs(f[1] - f[0]).max() <= 1e-9 * fs
+    assert np.abs(f[2] - f[0][perm]).max() <= 1e-9 * fs
+    assert np.abs(f[0].sum(0)).max() <= 1e-9 * fs
+
+
+def test_hmc_is_time_reversible_in_energy(nm, orc):
+    """velocity Verlet property at full size: halving dt divides the mean |dH| of a trajectory by ~4 (checked through
+    the acceptance statistics: smaller dt never lowers the acceptance)"""
+    n_side, n = 5, 500
+    x, box = _configs(orc, n_side, [0.9], [0.08], seed=91)
+    acc = []
+    for dt in (0.008, 0.004, 0.002):
+        with nm.Engine(natoms=n, n_rep=1, nt=1, mod=48, ppos=0.0, pvol=0.0, text_rounding=False, seed=3) as eng:
+            eng.set_labels([1.2], [1.0], [1.2], [1.2])
+            eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[0.03], dv=[0.03], dt=[dt])
+            eng.run_cycle(0)
+            th = eng.get_thermo()[0]
+        assert th[13] == 48
+        acc.append(th[14])
+    assert acc[0] <= acc[1] + 4 and acc[1] <= acc[2] + 4 and acc[2] >= 30
