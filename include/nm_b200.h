@@ -184,6 +184,8 @@ int  nm_reset_counters(nm_engine* h);
 int64_t nm_launch_count(nm_engine* h);
 /* SM clocks each local slot's CTA spent in the last cycle kernel (load-balance diagnostics): out[n_rep] */
 int  nm_get_cta_clocks(nm_engine* h, uint64_t* out);
+/* the last cycle's counters of each local slot (diagnostics): out[n_rep][NM_COUNTER_WIDTH] */
+int  nm_get_replica_counters(nm_engine* h, uint64_t* out);
 
 /* ---- a-14: calculate_rdf (lammps_distr.py:123-135) over a batch of samples.
  *   pos   : HOST or DEVICE float32 [nsamples][natoms][3] (dev_ptrs selects which)

@@ -54,6 +54,7 @@ struct Dev {
   double *list_pairs;                      // [nrep] listed unordered pairs of the current list
   int *cfg_slot, *slot_cfg;                // local permutation
   unsigned long long* cta_clk;             // [nrep] SM clocks the configuration's CTA spent in the last cycle
+  unsigned long long* rep_ct;              // [nrep][NM_COUNTER_WIDTH] the last cycle's counters of each configuration
   int* order;                              // [nrep] blockIdx -> configuration (cost-balanced placement)
   int *status;                             // [nrep]
   // per local slot
@@ -73,6 +74,7 @@ struct Ctx {
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
   uint16_t *cell_atoms, *atom_cell;
+  uint2* gtab;                  // shared (SMALL mode): [8][nthr] per-thread {cursor, image-code bits} of the 8 image groups
   unsigned long long* s_pairs;  // shared: in-cutoff ordered pairs of force-only evaluations
   // global views of this configuration
   double *gx, *gv, *gf, *gxs, *gvs, *gfs, *gx0;
@@ -88,13 +90,13 @@ struct Ctx {
 
 // rows are padded to an odd number of words: consecutive atoms (lanes) then hit different banks
 __host__ __device__ inline size_t hbits_words(int N) { const size_t w = (N + 31) / 32; return w * 32 * (w | 1); }
-__host__ __device__ inline size_t smem_bytes(int Npad, int N, int small) {
+__host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nthr) {
   size_t b = sizeof(double) * (3 * (size_t)Npad + RED_DOUBLES + BC_DOUBLES + SHT_DOUBLES);
   b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8 + 2);   // +2: keeps the float4 block 16-byte aligned
   b += sizeof(float4) * (size_t)Npad;
   b += sizeof(unsigned long long) * 2;
   b += sizeof(uint16_t) * 2 * (size_t)Npad;
-  if (small) b += sizeof(uint32_t) * hbits_words(N);
+  if (small) b += sizeof(uint32_t) * (hbits_words(N) + (hbits_words(N) & 1)) + sizeof(uint2) * 8 * (size_t)nthr;
   return b;
 }
 
@@ -114,6 +116,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   uint16_t* h = reinterpret_cast<uint16_t*>(q);
   cx.cell_atoms = h; cx.atom_cell = h + d.Npad;
   cx.hbits = reinterpret_cast<uint32_t*>(h + 2 * d.Npad);
+  cx.gtab = reinterpret_cast<uint2*>(cx.hbits + hbits_words(d.N) + (hbits_words(d.N) & 1));   // SMALL mode only
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
   cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off; cx.gx0 = d.x0 + off;
@@ -396,6 +399,97 @@ __device__ int extract_rows_small(const Dev& d, Ctx& cx) {
   return over;
 }
 
+// SMALL mode extraction, box >= ~2.3 r_list (the usual case). The image group of a listed pair follows from 16
+// position bins per axis: a listed pair is separated by < 7/16 (same image) or > 9/16 (adjacent image) of the box
+// along every axis, so "wrapped along a" <=> the bins differ by >= 8. bin_masks() leaves, per axis and bin b, the
+// bit row of the atoms whose bin differs from b by >= 8; the owner of row i then
+//   pass 1: gets its 8 group sizes from 8 popcounts per 32-bit word of its hit row (inclusion-exclusion), and
+//   pass 2: walks the set bits once (flattened walk: a warp iterates max(hits) times), reads the group of a hit
+//           from three mask bits and stores the index straight into its final slot of the [quad][atom] layout
+//           through a per-thread cursor table in shared memory.
+__device__ void bin_masks(Ctx& cx) {
+  const int N = cx.N, W = (N + 31) / 32, WS = W | 1;
+  uint32_t* M = reinterpret_cast<uint32_t*>(cx.cell_cnt);          // [3][16][WS] (the cell arrays are idle in SMALL mode)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int w = wid; w < W; w += nw) {
+    const int j = w * 32 + lane;
+    const float4 p = cx.sf[j < cx.Npad ? j : cx.Npad - 1];
+    const int b[3] = { min(15, (int)(p.x * 16.f)), min(15, (int)(p.y * 16.f)), min(15, (int)(p.z * 16.f)) };
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const uint32_t m = __ballot_sync(0xffffffffu, k < 8 ? b[a] >= k + 8 : b[a] <= k - 8);
+        if (lane == 0) M[(a * 16 + k) * WS + w] = m;
+      }
+  }
+}
+
+__device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
+  const int N = cx.N, Npad = cx.Npad, W = (N + 31) / 32, WS = W | 1, nthr = blockDim.x;
+  const double invL = 1.0 / cx.L;
+  const uint32_t* M = reinterpret_cast<const uint32_t*>(cx.cell_cnt);
+  uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
+  uint2* tab = cx.gtab + threadIdx.x;                      // entry of group g: tab[g * nthr]
+  const unsigned qstride = (unsigned)Npad * 4u;            // 16-bit entries per quad row
+  int over = 0; double tot = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float4 pi = cx.sf[i];
+    const uint32_t* row = cx.hbits + (size_t)i * WS;
+    const int bx = min(15, (int)(pi.x * 16.f)), by = min(15, (int)(pi.y * 16.f)), bz = min(15, (int)(pi.z * 16.f));
+    const uint32_t *MX = M + bx * WS, *MY = M + (16 + by) * WS, *MZ = M + (32 + bz) * WS;
+    int nT = 0, nX = 0, nY = 0, nZ = 0, nXY = 0, nXZ = 0, nYZ = 0, nXYZ = 0;
+    for (int w = 0; w < W; w++) {
+      const uint32_t m = row[w], X = MX[w] & m, Y = MY[w], Z = MZ[w];
+      nT += __popc(m); nX += __popc(X); nY += __popc(m & Y); nZ += __popc(m & Z);
+      nXY += __popc(X & Y); nXZ += __popc(X & Z); nYZ += __popc(m & Y & Z); nXYZ += __popc(X & Y & Z);
+    }
+    const int cg[8] = { nT - nX - nY - nZ + nXY + nXZ + nYZ - nXYZ, nX - nXY - nXZ + nXYZ, nY - nXY - nYZ + nXYZ, nXY - nXYZ,
+                        nZ - nXZ - nYZ + nXYZ, nXZ - nXYZ, nYZ - nXYZ, nXYZ };
+    // image code of group g: -1 along an axis for atoms in the lower half of the box, +1 in the upper half
+    const int sx = bx < 8 ? -1 : 1, sy = by < 8 ? -1 : 1, sz = bz < 8 ? -1 : 1;
+    int run = 0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+      const int code = 13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz;
+      tab[g * nthr] = make_uint2((unsigned)run, (unsigned)((code & 7) << 13) | ((unsigned)((code >> 3) << 13) << 16));
+      run += (cg[g] + 3) & ~3;
+    }
+    const int nq = run >> 2;
+    if (nq > d.maxq) { over = 1; cx.nnb[i] = 0; continue; }
+    uint16_t* li = l16 + (size_t)i * 4;
+    auto put = [&](unsigned pos, unsigned j, unsigned cw) {
+      const unsigned slot = pos & 3u;
+      const unsigned cb = slot < 2u ? (cw >> (16u * slot)) & 0xe000u : 0u;
+      li[(pos >> 2) * qstride + slot] = (uint16_t)(j | cb);
+    };
+    {
+      int w = 0; uint32_t m = row[0];
+      for (;;) {
+        while (m == 0u && ++w < W) m = row[w];
+        if (w >= W) break;
+        const int b = __ffs(m) - 1; m &= m - 1;
+        const unsigned g = ((MX[w] >> b) & 1u) | (((MY[w] >> b) & 1u) << 1) | (((MZ[w] >> b) & 1u) << 2);
+        uint2* e = tab + g * nthr;
+        const uint2 t = *e;
+        e->x = t.x + 1u;
+        put(t.x, (unsigned)(w * 32 + b), t.y);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g++)                              // pad every group to a whole quad with the dummy atom
+      if (cg[g]) { const uint2 t = tab[g * nthr]; for (unsigned pos = t.x; pos & 3u; pos++) put(pos, (unsigned)N, t.y); }
+    cx.nnb[i] = (uint16_t)nq;
+    cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+    tot += nT;
+  }
+  double r[1] = { tot };
+  block_sum<1>(r, cx.red);
+  cx.list_pairs = 0.5 * r[0];
+  return over;
+}
+
+
 // re-wrap every atom into [0,L) (shifting the revert copy by the same lattice vector) and refresh the float32
 // fractional copies; entries N..Npad-1 are parked far away so that padded indices never test positive
 __device__ void wrap_and_refresh(Ctx& cx, bool wrap) {
@@ -429,7 +523,9 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
   const float magic = 12582912.f;
   const int ntile = W * (W + 1) / 2;
+  const bool bins = !cx.mic && rl * invL * (1.0 + 1e-3) < 0.43;     // see extract_rows_bins
   const long long t_tiles0 = clock64();
+  if (bins) bin_masks(cx);
   for (int t = wid; t < ntile; t += nw) {
     int ti = 0, rem = t;                      // tile (ti, tj), ti <= tj, enumerated row by row
     while (rem >= W - ti) { rem -= W - ti; ti++; }
@@ -453,7 +549,7 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
   }
   __syncthreads();
   if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t_tiles0);
-  const int over = extract_rows_small(d, cx);
+  const int over = bins ? extract_rows_bins(d, cx) : extract_rows_small(d, cx);
   if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
   cx.L0 = L; cx.L0o = L;
   update_thr(d, cx);
@@ -635,13 +731,10 @@ __device__ void check_list(const Dev& d, Ctx& cx) {
 }
 
 // ------------------------------------------------------------------ a-1: LJ lj/cut evaluation off the list
-// EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
-// half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
-// Ends with a barrier: shared positions may be rewritten afterwards.
-// one listed pair, image already resolved (xs = x_i - image shift of the quad): rsq, reciprocal by MUFU.RCP64H +
-// one cubic Newton step, LJ force. The cutoff test is a 64-bit INTEGER compare (positive doubles order like
-// integers) and the masking a single select on the high word, so only arithmetic reaches the FP64 pipe:
-// 19 FP64-pipe instructions per pair for forces, +3 for energy and virial.
+// one listed pair, image already resolved (xs = x_i - image shift of the quad): rsq, reciprocal from an FP32
+// MUFU.RCP seed + one FP64 Newton step, LJ force. The cutoff test is a 64-bit INTEGER compare (positive doubles
+// order like integers) and the masking a single select on the high word, so only arithmetic reaches the FP64 pipe:
+// 16 FP64-pipe instructions per pair for forces, +4 for energy and virial.
 // MIC: small boxes -- the minimum image is taken per pair (high-word test + FP64 subtract) instead.
 template <bool EW, bool MIC>
 __device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs, double ys, double zs,
@@ -650,7 +743,6 @@ __device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs
   double dx = xs - pj[0], dy = ys - pj[1], dz = zs - pj[2];
   if (MIC) { dx = mic_fast(dx, L_hi, L_lo, hL_hi); dy = mic_fast(dy, L_hi, L_lo, hL_hi); dz = mic_fast(dz, L_hi, L_lo, hL_hi); }
   const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-  const bool in = __double_as_longlong(rsq) < rc2_bits;
 #ifndef NM_RCP_EXACT      // default: FP32-seeded reciprocal; -DNM_RCP_EXACT selects the < 1 ulp variant
   float yf;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)rsq));   // 22-bit seed from the FP32 special-function unit
@@ -668,16 +760,23 @@ __device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs
 #endif
   const double r6inv = r2inv * r2inv * r2inv;
   double fpair = r6inv * fma(48.0, r6inv, -24.0) * r2inv;
-  // outside the cutoff the high word is zeroed: the operand becomes a denormal (< 1e-308) whose products vanish
-  fpair = __hiloint2double(in ? __double2hiint(fpair) : 0, __double2loint(fpair));
-  fx = fma(dx, fpair, fx); fy = fma(dy, fpair, fy); fz = fma(dz, fpair, fz);
-  np += in;
+  // outside the cutoff the high word is zeroed: the operand becomes a denormal (< 1e-308) whose products vanish.
+  // One predicate drives the select(s) and the pair count.
+  int fh = __double2hiint(fpair);
   if (EW) {
-    double ep = r6inv * fma(4.0, r6inv, -4.0);
-    ep = __hiloint2double(in ? __double2hiint(ep) : 0, __double2loint(ep));
-    e += ep;
+    const double ep = r6inv * fma(4.0, r6inv, -4.0);
+    int eh = __double2hiint(ep);
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s64 p, %3, %4;\n\tselp.b32 %0, %0, 0, p;\n\tselp.b32 %1, %1, 0, p;\n\t@p add.s32 %2, %2, 1;\n\t}"
+        : "+r"(fh), "+r"(eh), "+r"(np) : "l"(__double_as_longlong(rsq)), "l"(rc2_bits));
+    fpair = __hiloint2double(fh, __double2loint(fpair));
+    e += __hiloint2double(eh, __double2loint(ep));
     vir = fma(rsq, fpair, vir);
+  } else {
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s64 p, %2, %3;\n\tselp.b32 %0, %0, 0, p;\n\t@p add.s32 %1, %1, 1;\n\t}"
+        : "+r"(fh), "+r"(np) : "l"(__double_as_longlong(rsq)), "l"(rc2_bits));
+    fpair = __hiloint2double(fh, __double2loint(fpair));
   }
+  fx = fma(dx, fpair, fx); fy = fma(dy, fpair, fy); fz = fma(dz, fpair, fz);
 }
 
 // EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
@@ -694,21 +793,26 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
     const double xi = cx.sp[3 * i], yi = cx.sp[3 * i + 1], zi = cx.sp[3 * i + 2];
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const int nq = cx.nnb[i];
-    const ushort4* lp = cx.list + i;
-    ushort4 cur = nq > 0 ? lp[0] : make_ushort4(0, 0, 0, 0);
+    // the list is walked with one byte pointer (row stride Npad quads); the next quad is loaded and the one after
+    // it pulled into L1 unconditionally: the allocation carries two spare rows, rows past nq are never used
+    const char* lp = reinterpret_cast<const char*>(cx.list + i);
+    const unsigned stride = (unsigned)Npad * 8u;
+    uint2 cur = *reinterpret_cast<const uint2*>(lp);
+    lp += stride;
     for (int q = 0; q < nq; q++) {
-      // the quad two iterations ahead is pulled into L1 (no register cost); the next one is loaded here
-      if (q + 2 < nq) asm volatile("prefetch.global.L1 [%0];" :: "l"(lp + (size_t)(q + 2) * Npad));
-      const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
+      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);
+      lp += stride;
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(lp));
       double xs = xi, ys = yi, zs = zi;
       if (!MIC) {
-        const int code = (cur.x >> 13) | ((cur.y >> 13) << 3);
-        xs -= cx.sht[3 * code]; ys -= cx.sht[3 * code + 1]; zs -= cx.sht[3 * code + 2];
+        const unsigned code = ((cur.x >> 13) & 7u) | ((cur.x >> 26) & 0x38u);
+        const double* sh = cx.sht + 3 * code;
+        xs -= sh[0]; ys -= sh[1]; zs -= sh[2];
       }
-      lj_pair<EW, MIC>(cx.sp + 3 * (cur.x & 0x1fff), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(cx.sp + 3 * (cur.y & 0x1fff), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(cx.sp + 3 * cur.z, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(cx.sp + 3 * cur.w, xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * (cur.x & 0x1fffu), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * ((cur.x >> 16) & 0x1fffu), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * (cur.y & 0xffffu), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(cx.sp + 3 * (cur.y >> 16), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       cur = nxt;
     }
     if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_eval0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
@@ -1230,7 +1334,7 @@ k_cycle(Dev d, long long cycle) {
     // placement cost: a CTA that had its SM to itself ran ~1.4x faster than it would have next to a neighbour (measured)
     const bool solo = d.per_sm == 2 && d.nrep > d.nsm && d.nrep <= 2 * d.nsm && (int)blockIdx.x >= d.nrep - d.nsm && (int)blockIdx.x < d.nsm;
     d.cta_clk[c] = solo ? dt_cycle + dt_cycle * 2 / 5 : dt_cycle;
-    for (int k = 0; k < NM_COUNTER_WIDTH; k++) if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]);
+    for (int k = 0; k < NM_COUNTER_WIDTH; k++) { d.rep_ct[(size_t)c * NM_COUNTER_WIDTH + k] = cx.ct[k]; if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]); }
   }
 }
 
@@ -1460,19 +1564,19 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   h->threads = N <= 256 ? 256 : (N <= 512 ? 512 : 1024);   // 64 registers/thread: 32 warps per SM hide the FP64 latency
   d.f32 = cfg->precision == 32;
   d.small = N <= NSMALL;
-  h->smem = smem_bytes(d.Npad, N, d.small);
+  h->smem = smem_bytes(d.Npad, N, d.small, h->threads);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, cfg->device) == cudaSuccess) h->nsm = pr.multiProcessorCount; else h->nsm = 148; }
   d.nsm = h->nsm; d.per_sm = (h->smem * 2 <= 220 * 1024 && h->threads <= 512) ? 2 : 1;
   if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
   const size_t per = (size_t)nrep * 3 * d.Npad;
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, per);
-  DA(d.list, (size_t)nrep * d.maxq * d.Npad); DA(d.qcode, (size_t)nrep * d.maxq * d.Npad);
+  DA(d.list, ((size_t)nrep * d.maxq + 2) * d.Npad); DA(d.qcode, (size_t)nrep * d.maxq * d.Npad);
   DA(d.ltmp, (size_t)nrep * ((d.maxnbo + 3) & ~3) * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad); DA(d.micmode, nrep);
   DA(d.olist, (size_t)nrep * d.maxqo * d.Npad); DA(d.ocode, (size_t)nrep * d.maxqo * d.Npad); DA(d.onq, (size_t)nrep * d.Npad);
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
-  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.order, nrep);
+  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.order, nrep);
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
@@ -1716,6 +1820,18 @@ int nm_get_cta_clocks(nm_engine* h, uint64_t* out) {
   CK(cudaMemcpyAsync(cs.data(), h->d.cfg_slot, sizeof(int) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int c = 0; c < h->d.nrep; c++) out[cs[c]] = clk[c];
+  return NM_OK;
+}
+
+int nm_get_replica_counters(nm_engine* h, uint64_t* out) {
+  if (!h || !out) return fail(NM_EINVAL, "nm_get_replica_counters: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t W = NM_COUNTER_WIDTH;
+  std::vector<unsigned long long> ct(h->d.nrep * W); std::vector<int> cs(h->d.nrep);
+  CK(cudaMemcpyAsync(ct.data(), h->d.rep_ct, sizeof(unsigned long long) * ct.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(cs.data(), h->d.cfg_slot, sizeof(int) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < h->d.nrep; c++) for (size_t k = 0; k < W; k++) out[cs[c] * W + k] = ct[c * W + k];
   return NM_OK;
 }
 

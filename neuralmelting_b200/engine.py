@@ -62,6 +62,7 @@ def load_library():
         getattr(L, name).argtypes = [C.c_void_p]
     L.nm_launch_count.argtypes = [C.c_void_p]
     L.nm_get_cta_clocks.argtypes = [C.c_void_p, C.c_void_p]
+    L.nm_get_replica_counters.argtypes = [C.c_void_p, C.c_void_p]
     L.nm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.nm_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.nm_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
@@ -235,6 +236,12 @@ class Engine:
     def cta_clocks(self):
         out = np.zeros(self.n_rep, dtype=np.uint64)
         _check(self._L.nm_get_cta_clocks(self._h, _ptr(out)))
+        return out
+
+    def replica_counters(self):
+        """last cycle's counters per local slot: (n_rep, NM_COUNTER_WIDTH) uint64, columns as COUNTER_COLS"""
+        out = np.zeros((self.n_rep, COUNTER_WIDTH), dtype=np.uint64)
+        _check(self._L.nm_get_replica_counters(self._h, _ptr(out)))
         return out
 
 

@@ -54,6 +54,13 @@ def main():
     clk = eng.cta_clocks().astype(float).reshape(np_, nt) / 1e6
     print("per-slot Mclk by temperature (mean over P):", np.round(clk.mean(0), 1))
     print("per-slot Mclk min %.1f mean %.1f max %.1f" % (clk.min(), clk.mean(), clk.max()))
+    rc = eng.replica_counters().astype(float); ci = {k: i for i, k in enumerate(nm.COUNTER_COLS)}
+    order = np.argsort(-rc[:, ci["clk_total"]])
+    print("slot   T     rho   Mclk  sweeps hmc builds evals  Mclk_build Mclk_eval  pairs/eval")
+    for k in list(order[:12]) + list(order[-4:]):
+        r = rc[k]
+        print("%4d  %.2f  %.3f  %5.1f  %4d %4d  %4d  %5d   %6.1f  %6.1f   %7.0f" % (k, tt[k], n / th[k, 5], r[ci["clk_total"]] / 1e6, r[ci["sweeps"]], r[ci["hmc_moves"]],
+              r[ci["list_builds"]], r[ci["force_evals"]], r[ci["clk_build"]] / 1e6, r[ci["clk_eval"]] / 1e6, r[ci["list_pairs"]] / max(1, r[ci["force_evals"]])))
     print("T col0 thermo:", np.round(th[:nt, :6], 3)[::max(1, nt // 4)])
 
 main()
