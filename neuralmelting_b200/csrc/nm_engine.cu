@@ -399,6 +399,10 @@ __device__ int extract_rows_small(const Dev& d, Ctx& cx) {
   return over;
 }
 
+__device__ __forceinline__ uint32_t lds_u32(unsigned a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_u64(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(unsigned a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
 // SMALL mode extraction, box >= ~2.3 r_list (the usual case). The image group of a listed pair follows from 16
 // position bins per axis: a listed pair is separated by < 7/16 (same image) or > 9/16 (adjacent image) of the box
 // along every axis, so "wrapped along a" <=> the bins differ by >= 8. bin_masks() leaves, per axis and bin b, the
@@ -431,7 +435,6 @@ __device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
   const uint32_t* M = reinterpret_cast<const uint32_t*>(cx.cell_cnt);
   uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
   uint2* tab = cx.gtab + threadIdx.x;                      // entry of group g: tab[g * nthr]
-  const unsigned qstride = (unsigned)Npad * 4u;            // 16-bit entries per quad row
   int over = 0; double tot = 0.0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const float4 pi = cx.sf[i];
@@ -457,23 +460,30 @@ __device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
     }
     const int nq = run >> 2;
     if (nq > d.maxq) { over = 1; cx.nnb[i] = 0; continue; }
-    uint16_t* li = l16 + (size_t)i * 4;
+    // pass 2 runs on explicit 32-bit shared addresses (no generic-pointer arithmetic inside the loop)
+    char* li = reinterpret_cast<char*>(l16 + (size_t)i * 4);
+    asm volatile("" : "+l"(li));                            // keep the row base in registers (ptxas rematerialises it per store)
+    const unsigned rowbytes = (unsigned)Npad * 8u, gbytes = (unsigned)nthr * 8u;
+    const unsigned row_s = (unsigned)__cvta_generic_to_shared(row), mx_s = (unsigned)__cvta_generic_to_shared(MX),
+                   my_s = (unsigned)__cvta_generic_to_shared(MY), mz_s = (unsigned)__cvta_generic_to_shared(MZ),
+                   tab_s = (unsigned)__cvta_generic_to_shared(tab);
     auto put = [&](unsigned pos, unsigned j, unsigned cw) {
       const unsigned slot = pos & 3u;
-      const unsigned cb = slot < 2u ? (cw >> (16u * slot)) & 0xe000u : 0u;
-      li[(pos >> 2) * qstride + slot] = (uint16_t)(j | cb);
+      const unsigned cb = (unsigned)((unsigned long long)cw >> (slot * 16u)) & 0xe000u;   // slots 2, 3 shift the bits out
+      *reinterpret_cast<uint16_t*>(li + (pos >> 2) * rowbytes + slot * 2u) = (uint16_t)(j | cb);
     };
     {
-      int w = 0; uint32_t m = row[0];
+      int w = 0; unsigned jb = 0u;
+      uint32_t m = lds_u32(row_s), X = lds_u32(mx_s), Y = lds_u32(my_s), Z = lds_u32(mz_s);
       for (;;) {
-        while (m == 0u && ++w < W) m = row[w];
+        while (m == 0u && ++w < W) { m = lds_u32(row_s + 4u * w); X = lds_u32(mx_s + 4u * w); Y = lds_u32(my_s + 4u * w); Z = lds_u32(mz_s + 4u * w); jb = 32u * w; }
         if (w >= W) break;
-        const int b = __ffs(m) - 1; m &= m - 1;
-        const unsigned g = ((MX[w] >> b) & 1u) | (((MY[w] >> b) & 1u) << 1) | (((MZ[w] >> b) & 1u) << 2);
-        uint2* e = tab + g * nthr;
-        const uint2 t = *e;
-        e->x = t.x + 1u;
-        put(t.x, (unsigned)(w * 32 + b), t.y);
+        const unsigned bit = (unsigned)__ffs(m) - 1u; m &= m - 1u;
+        const unsigned g = ((X >> bit) & 1u) | (((Y >> bit) & 1u) << 1) | (((Z >> bit) & 1u) << 2);
+        const unsigned ta = tab_s + g * gbytes;
+        const uint2 t = lds_u64(ta);
+        sts_u32(ta, t.x + 1u);
+        put(t.x, jb + bit, t.y);
       }
     }
 #pragma unroll
@@ -521,31 +531,40 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
   wrap_and_refresh(cx, true);
   __syncthreads();
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
-  const float magic = 12582912.f;
-  const int ntile = W * (W + 1) / 2;
+    const int ntile = W * (W + 1) / 2;
   const bool bins = !cx.mic && rl * invL * (1.0 + 1e-3) < 0.43;     // see extract_rows_bins
   const long long t_tiles0 = clock64();
   if (bins) bin_masks(cx);
+  const int WS = W | 1;
+  const uint32_t lastmask = (N & 31) ? (1u << (N & 31)) - 1u : 0xffffffffu;
   for (int t = wid; t < ntile; t += nw) {
     int ti = 0, rem = t;                      // tile (ti, tj), ti <= tj, enumerated row by row
     while (rem >= W - ti) { rem -= W - ti; ti++; }
     const int tj = ti + rem;
-    const int i = ti * 32 + lane;
-    const float4 pi = cx.sf[i < cx.Npad ? i : cx.Npad - 1];
-    uint32_t mask = 0, colmask = 0;
+    const int i = ti * 32 + lane;             // < Npad (Npad >= 32 W); rows >= N are never read
+    const float4 pi = cx.sf[i];
+    // explicit 32-bit shared addresses: immediate offsets for the 32 broadcast loads, one add per column store
+    const unsigned pj_s = (unsigned)__cvta_generic_to_shared(cx.sf + tj * 32);
+    unsigned col_s = (unsigned)__cvta_generic_to_shared(cx.hbits + (size_t)(tj * 32) * WS + ti);
+    const bool wcol = lane == 0 && ti != tj;
+    uint32_t mask = 0;
+    // fractional coordinates lie in [0,1]: the nearest-image distance along an axis is min(|d|, 1 - |d|), the same
+    // value as d - rint(d) gives, in two instructions; the test is symmetric in (i, j) bit for bit
+#pragma unroll
     for (int jj = 0; jj < 32; jj++) {
-      const int j = tj * 32 + jj;
-      const float4 pj = cx.sf[j < cx.Npad ? j : cx.Npad - 1];
-      float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      dx -= __fadd_rn(__fadd_rn(dx, magic), -magic); dy -= __fadd_rn(__fadd_rn(dy, magic), -magic); dz -= __fadd_rn(__fadd_rn(dz, magic), -magic);
-      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      const bool hit = r2 < rl2f && i != j && i < N && j < N;
-      const uint32_t col = __ballot_sync(0xffffffffu, hit);
-      mask |= hit ? (1u << jj) : 0u;
-      colmask = lane == jj ? col : colmask;
+      float4 pj;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(pj.w) : "r"(pj_s + 16u * jj));
+      float ax = fabsf(pi.x - pj.x), ay = fabsf(pi.y - pj.y), az = fabsf(pi.z - pj.z);
+      ax = fminf(ax, 1.f - ax); ay = fminf(ay, 1.f - ay); az = fminf(az, 1.f - az);
+      const bool hit = fmaf(az, az, fmaf(ay, ay, ax * ax)) < rl2f;
+      const uint32_t col = __ballot_sync(0xffffffffu, hit);   // column jj of the tile = row (tj*32+jj), word ti
+      if (hit) mask |= 1u << jj;
+      if (wcol) sts_u32(col_s, col);
+      col_s += 4u * WS;
     }
-    cx.hbits[(size_t)i * (W | 1) + tj] = mask;
-    if (ti != tj) cx.hbits[(size_t)(tj * 32 + lane) * (W | 1) + ti] = colmask;
+    if (tj == W - 1) mask &= lastmask;        // padded columns
+    if (ti == tj) mask &= ~(1u << lane);      // self
+    cx.hbits[(size_t)i * WS + tj] = mask;
   }
   __syncthreads();
   if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t_tiles0);
@@ -790,19 +809,19 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
   double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
   const long long t_eval0 = clock64();
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const long long t_atom0 = clock64();
     const double xi = cx.sp[3 * i], yi = cx.sp[3 * i + 1], zi = cx.sp[3 * i + 2];
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const int nq = cx.nnb[i];
-    // the list is walked with one byte pointer (row stride Npad quads); the next quad is loaded and the one after
-    // it pulled into L1 unconditionally: the allocation carries two spare rows, rows past nq are never used
+    // the list is walked with one byte pointer (row stride Npad quads); the next quad is loaded unconditionally:
+    // the allocation carries two spare rows, rows past nq are never used
     const char* lp = reinterpret_cast<const char*>(cx.list + i);
     const unsigned stride = (unsigned)Npad * 8u;
     uint2 cur = *reinterpret_cast<const uint2*>(lp);
     lp += stride;
     for (int q = 0; q < nq; q++) {
-      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);
+      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // one iteration (~2000 clocks) ahead of its use
       lp += stride;
-      asm volatile("prefetch.global.L1 [%0];" :: "l"(lp));
       double xs = xi, ys = yi, zs = zi;
       if (!MIC) {
         const unsigned code = ((cur.x >> 13) & 7u) | ((cur.x >> 26) & 0x38u);
@@ -815,7 +834,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       lj_pair<EW, MIC>(cx.sp + 3 * (cur.y >> 16), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       cur = nxt;
     }
-    if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_eval0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
+    if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_atom0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
     cx.gf[i] = fx; cx.gf[Npad + i] = fy; cx.gf[2 * Npad + i] = fz;
     if (KICK) {
       const double vx = fma(dtf, fx, cx.gv[i]), vy = fma(dtf, fy, cx.gv[Npad + i]), vz = fma(dtf, fz, cx.gv[2 * Npad + i]);
@@ -854,17 +873,19 @@ __device__ void eval_forces_f32(const Dev& d, Ctx& cx, double dtf, double (&out)
     const float4 pi = cx.sf[i];
     float fx = 0.f, fy = 0.f, fz = 0.f;
     const int nq = cx.nnb[i];
-    const ushort4* lp = cx.list + i;
-    ushort4 cur = nq > 0 ? lp[0] : make_ushort4(0, 0, 0, 0);
+    const char* lp = reinterpret_cast<const char*>(cx.list + i);
+    const unsigned stride = (unsigned)Npad * 8u;
+    uint2 cur = *reinterpret_cast<const uint2*>(lp);
+    lp += stride;
     for (int q = 0; q < nq; q++) {
-      if (q + 2 < nq) asm volatile("prefetch.global.L1 [%0];" :: "l"(lp + (size_t)(q + 2) * Npad));
-      const ushort4 nxt = (q + 1 < nq) ? lp[(size_t)(q + 1) * Npad] : cur;
+      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);
+      lp += stride;
       float xs = pi.x, ys = pi.y, zs = pi.z;
       if (!MIC) {
-        const int code = (cur.x >> 13) | ((cur.y >> 13) << 3);
+        const int code = (int)(((cur.x >> 13) & 7u) | ((cur.x >> 26) & 0x38u));
         xs -= (float)(code / 9 - 1); ys -= (float)((code / 3) % 3 - 1); zs -= (float)(code % 3 - 1);
       }
-      const int jj[4] = { cur.x & 0x1fff, cur.y & 0x1fff, cur.z, cur.w };
+      const unsigned jj[4] = { cur.x & 0x1fffu, (cur.x >> 16) & 0x1fffu, cur.y & 0xffffu, cur.y >> 16 };
 #pragma unroll
       for (int t = 0; t < 4; t++) {
         const float4 pj = cx.sf[jj[t]];
