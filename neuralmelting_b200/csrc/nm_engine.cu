@@ -750,10 +750,10 @@ __device__ void check_list(const Dev& d, Ctx& cx) {
 }
 
 // ------------------------------------------------------------------ a-1: LJ lj/cut evaluation off the list
-// one listed pair, image already resolved (xs = x_i - image shift of the quad): rsq, reciprocal from an FP32
-// MUFU.RCP seed + one FP64 Newton step, LJ force. The cutoff test is a 64-bit INTEGER compare (positive doubles
+// one listed pair, image already resolved (xs = x_i - image shift of the quad): rsq, reciprocal from the
+// MUFU.RCP64H seed + one cubic FP64 step, LJ force. The cutoff test is a 64-bit INTEGER compare (positive doubles
 // order like integers) and the masking a single select on the high word, so only arithmetic reaches the FP64 pipe:
-// 16 FP64-pipe instructions per pair for forces, +4 for energy and virial.
+// 17 FP64-pipe instructions per pair for forces, +4 for energy and virial.
 // MIC: small boxes -- the minimum image is taken per pair (high-word test + FP64 subtract) instead.
 template <bool EW, bool MIC>
 __device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs, double ys, double zs,
@@ -762,20 +762,25 @@ __device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs
   double dx = xs - pj[0], dy = ys - pj[1], dz = zs - pj[2];
   if (MIC) { dx = mic_fast(dx, L_hi, L_lo, hL_hi); dy = mic_fast(dy, L_hi, L_lo, hL_hi); dz = mic_fast(dz, L_hi, L_lo, hL_hi); }
   const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-#ifndef NM_RCP_EXACT      // default: FP32-seeded reciprocal; -DNM_RCP_EXACT selects the < 1 ulp variant
+  // reciprocal: MUFU.RCP64H seed (2^-19.9, measured) + one cubic step (3 DFMA): relative error ~ 2^-59.
+  // Measured alternatives: FP32 MUFU.RCP seed + one Newton step (-DNM_RCP_F32SEED; the two F64<->F32 conversions
+  // cost two issue slots each: 3 % slower, 6e-14); cubic + quadratic step (-DNM_RCP_EXACT, < 1 ulp, 3 % slower)
+#if defined(NM_RCP_F32SEED)
   float yf;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)rsq));   // 22-bit seed from the FP32 special-function unit
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)rsq));
   double y = (double)yf;
   double t = fma(-rsq, y, 1.0);
-  const double r2inv = fma(y, t, y);                    // one Newton step: relative error < 6e-14
+  const double r2inv = fma(y, t, y);
 #else
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
-  double t = fma(-rsq, y, 1.0);                         // seed is good to 2^-19.9 (measured): cubic step, then a quadratic one
+  double t = fma(-rsq, y, 1.0);
   t = fma(t, t, t);
+#if defined(NM_RCP_EXACT)
   y = fma(y, t, y);
   t = fma(-rsq, y, 1.0);
-  const double r2inv = fma(y, t, y);                    // relative error ~ seed^6 (< 1 ulp)
+#endif
+  const double r2inv = fma(y, t, y);
 #endif
   const double r6inv = r2inv * r2inv * r2inv;
   double fpair = r6inv * fma(48.0, r6inv, -24.0) * r2inv;
@@ -813,14 +818,14 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
     const double xi = cx.sp[3 * i], yi = cx.sp[3 * i + 1], zi = cx.sp[3 * i + 2];
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const int nq = cx.nnb[i];
-    // the list is walked with one byte pointer (row stride Npad quads); the next quad is loaded unconditionally:
+    // the list is walked with one byte pointer (row stride Npad quads); quads are loaded unconditionally:
     // the allocation carries two spare rows, rows past nq are never used
     const char* lp = reinterpret_cast<const char*>(cx.list + i);
     const unsigned stride = (unsigned)Npad * 8u;
     uint2 cur = *reinterpret_cast<const uint2*>(lp);
     lp += stride;
     for (int q = 0; q < nq; q++) {
-      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // one iteration (~2000 clocks) ahead of its use
+      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // for the next iteration
       lp += stride;
       double xs = xi, ys = yi, zs = zi;
       if (!MIC) {
