@@ -112,7 +112,9 @@ __device__ __forceinline__ double rcp_nr(double x) {
 }
 
 // ---------------------------------------------------------------- block reductions (deterministic order)
-// red: shared scratch of at least 32*K + K doubles. All threads get the totals.
+// red: shared scratch of 32*K doubles that no thread is still reading (callers alternate between two scratch areas,
+// so one barrier per reduction suffices). Warp butterflies, one partial per warp, then every warp reduces the
+// partials with the same butterfly: all threads get bitwise identical totals, independent of scheduling.
 template <int K>
 __device__ __forceinline__ void block_sum(double (&v)[K], double* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -121,20 +123,18 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
   }
-  __syncthreads();                       // scratch free (previous readers done)
   if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < K; k++) red[wid * K + k] = v[k];
-  }
-  __syncthreads();
-  if (threadIdx.x < K) {
-    double s = 0.0;
-    for (int w = 0; w < nw; w++) s += red[w * K + threadIdx.x];
-    red[32 * K + threadIdx.x] = s;
+    for (int k = 0; k < K; k++) red[k * 32 + wid] = v[k];
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < K; k++) v[k] = red[32 * K + k];
+  for (int k = 0; k < K; k++) {
+    double p = lane < nw ? red[k * 32 + lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    v[k] = p;
+  }
 }
 
 }  // namespace nm

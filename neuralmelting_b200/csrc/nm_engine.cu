@@ -21,7 +21,8 @@
 namespace nm {
 
 constexpr int NCMAX = 12;                // cell grid is at most 12^3
-constexpr int RED_DOUBLES = 32 * 12 + 12;
+constexpr int RED_HALF = 32 * 12;          // one block_sum scratch area (K <= 12)
+constexpr int RED_DOUBLES = 2 * RED_HALF;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
 constexpr int NSMALL = 768;              // largest N handled by the all-pairs hit-matrix build (72 KB of bits)
@@ -86,6 +87,7 @@ struct Ctx {
   unsigned long long ct[NM_COUNTER_WIDTH];   // meaningful on thread 0 only
   double list_pairs;
   int status;
+  int redflip;                  // which half of `red` the next block_sum uses
 };
 
 // rows are padded to an odd number of words: consecutive atoms (lanes) then hit different banks
@@ -100,7 +102,15 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
   return b;
 }
 
+// block_sum on alternating scratch halves (see nm_device.cuh): one barrier per reduction
+template <int K>
+__device__ __forceinline__ void bsum(double (&v)[K], Ctx& cx) {
+  cx.redflip ^= 1;
+  block_sum<K>(v, cx.red + cx.redflip * RED_HALF);
+}
+
 __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned char* smem) {
+  cx.redflip = 0;
   cx.N = d.N; cx.Npad = d.Npad; cx.c = c;
   double* p = reinterpret_cast<double*>(smem);
   cx.sp = p; p += 3 * d.Npad;
@@ -308,7 +318,7 @@ __device__ int grouped_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
   }
   if (BITS) {
     double r[1] = { tot };
-    block_sum<1>(r, cx.red);
+    bsum<1>(r, cx);
     cx.list_pairs = 0.5 * r[0];
   }
   return over;
@@ -394,13 +404,16 @@ __device__ int extract_rows_small(const Dev& d, Ctx& cx) {
     tot += cnt;
   }
   double r[1] = { tot };
-  block_sum<1>(r, cx.red);
+  bsum<1>(r, cx);
   cx.list_pairs = 0.5 * r[0];
   return over;
 }
 
 __device__ __forceinline__ uint32_t lds_u32(unsigned a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds_u64(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void lds_f64x3(unsigned a, double& x, double& y, double& z) {
+  asm volatile("ld.shared.f64 %0, [%3];\n\tld.shared.f64 %1, [%3+8];\n\tld.shared.f64 %2, [%3+16];" : "=d"(x), "=d"(y), "=d"(z) : "r"(a));
+}
 __device__ __forceinline__ void sts_u32(unsigned a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 
 // SMALL mode extraction, box >= ~2.3 r_list (the usual case). The image group of a listed pair follows from 16
@@ -494,7 +507,7 @@ __device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
     tot += nT;
   }
   double r[1] = { tot };
-  block_sum<1>(r, cx.red);
+  bsum<1>(r, cx);
   cx.list_pairs = 0.5 * r[0];
   return over;
 }
@@ -703,7 +716,7 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
     cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
   }
   double r[2] = { tot, (double)over };
-  block_sum<2>(r, cx.red);
+  bsum<2>(r, cx);
   cx.list_pairs = 0.5 * r[0];
   if (r[1] > 0.0) cx.status |= ST_NEIGH;
   cx.L0 = L;
@@ -756,10 +769,10 @@ __device__ void check_list(const Dev& d, Ctx& cx) {
 // 17 FP64-pipe instructions per pair for forces, +4 for energy and virial.
 // MIC: small boxes -- the minimum image is taken per pair (high-word test + FP64 subtract) instead.
 template <bool EW, bool MIC>
-__device__ __forceinline__ void lj_pair(const double* __restrict__ pj, double xs, double ys, double zs,
+__device__ __forceinline__ void lj_pair(double xj, double yj, double zj, double xs, double ys, double zs,
                                         int L_hi, int L_lo, int hL_hi, long long rc2_bits,
                                         double& fx, double& fy, double& fz, int& np, double& e, double& vir) {
-  double dx = xs - pj[0], dy = ys - pj[1], dz = zs - pj[2];
+  double dx = xs - xj, dy = ys - yj, dz = zs - zj;
   if (MIC) { dx = mic_fast(dx, L_hi, L_lo, hL_hi); dy = mic_fast(dy, L_hi, L_lo, hL_hi); dz = mic_fast(dz, L_hi, L_lo, hL_hi); }
   const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
   // reciprocal: MUFU.RCP64H seed (2^-19.9, measured) + one cubic step (3 DFMA): relative error ~ 2^-59.
@@ -821,7 +834,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
     // the list is walked with one byte pointer (row stride Npad quads); quads are loaded unconditionally:
     // the allocation carries two spare rows, rows past nq are never used
     const char* lp = reinterpret_cast<const char*>(cx.list + i);
-    const unsigned stride = (unsigned)Npad * 8u;
+    const unsigned stride = (unsigned)Npad * 8u, sp_s = (unsigned)__cvta_generic_to_shared(cx.sp);
     uint2 cur = *reinterpret_cast<const uint2*>(lp);
     lp += stride;
     for (int q = 0; q < nq; q++) {
@@ -833,10 +846,16 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
         const double* sh = cx.sht + 3 * code;
         xs -= sh[0]; ys -= sh[1]; zs -= sh[2];
       }
-      lj_pair<EW, MIC>(cx.sp + 3 * (cur.x & 0x1fffu), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(cx.sp + 3 * ((cur.x >> 16) & 0x1fffu), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(cx.sp + 3 * (cur.y & 0xffffu), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(cx.sp + 3 * (cur.y >> 16), xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      // explicit 32-bit shared addresses (one IMAD per neighbour). ptxas places each gather next to its use
+      // whatever the source order (volatile loads up front were tried: same schedule)
+      const unsigned a0 = sp_s + 24u * (cur.x & 0x1fffu), a1 = sp_s + 24u * ((cur.x >> 16) & 0x1fffu),
+                     a2 = sp_s + 24u * (cur.y & 0xffffu), a3 = sp_s + 24u * (cur.y >> 16);
+      double p[12];
+      lds_f64x3(a0, p[0], p[1], p[2]); lds_f64x3(a1, p[3], p[4], p[5]); lds_f64x3(a2, p[6], p[7], p[8]); lds_f64x3(a3, p[9], p[10], p[11]);
+      lj_pair<EW, MIC>(p[0], p[1], p[2], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(p[3], p[4], p[5], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(p[6], p[7], p[8], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC>(p[9], p[10], p[11], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       cur = nxt;
     }
     if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_atom0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
@@ -849,7 +868,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
   }
   if (EW) {
     double r[4] = { 0.5 * e, 0.5 * vir, (double)np, ke };
-    block_sum<4>(r, cx.red);
+    bsum<4>(r, cx);
     out[0] = r[0]; out[1] = r[1]; out[2] = 0.5 * r[2]; out[3] = 0.5 * d.mass * r[3];
     if (threadIdx.x == 0) {
       cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_PAIRS_FULL] += (unsigned long long)out[2];
@@ -917,7 +936,7 @@ __device__ void eval_forces_f32(const Dev& d, Ctx& cx, double dtf, double (&out)
   }
   if (EW) {
     double r[4] = { 0.5 * (double)e, 0.5 * (double)vir, (double)np, ke };
-    block_sum<4>(r, cx.red);
+    bsum<4>(r, cx);
     out[0] = r[0]; out[1] = r[1]; out[2] = 0.5 * r[2]; out[3] = 0.5 * d.mass * r[3];
     if (threadIdx.x == 0) {
       cx.ct[NM_CT_FORCE_EVALS]++; cx.ct[NM_CT_PAIRS_FULL] += (unsigned long long)out[2];
@@ -1059,9 +1078,67 @@ __device__ void volume_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double
 // ------------------------------------------------------------------ a-4 velocity create + zero linear + zero angular
 // LAMMPS 'velocity all create T seed dist gaussian' (loop all, mom yes, rot no), then 'zero linear',
 // 'zero angular' (lammps_remcmc.py:604-606). Returns KE = 0.5 m sum v^2.
+// one atom per thread (N <= blockDim.x): the same arithmetic with the atom's velocity and wrapped position held in
+// registers across the six reductions (one global store at the end instead of five read-modify-write passes)
+__device__ double velocity_create_1(const Dev& d, Ctx& cx, const Rng& r, double t_target) {
+  const int N = cx.N, Npad = cx.Npad, i = threadIdx.x;
+  const bool own = i < N;
+  const double m = d.mass, inv = 1.0 / sqrt(m), inv_mN = 1.0 / (m * cx.N);
+  double vx = 0.0, vy = 0.0, vz = 0.0, px = 0.0, py = 0.0, pz = 0.0;
+  double s[4] = { 0, 0, 0, 0 };
+  if (own) {
+    double g[3]; rng_gauss3(r, (uint32_t)i, P_HMC_VEL, g);
+    vx = g[0] * inv; vy = g[1] * inv; vz = g[2] * inv;
+    s[0] += m * vx; s[1] += m * vy; s[2] += m * vz;
+    px = wrapg(cx.sp[3 * i], cx.L); py = wrapg(cx.sp[3 * i + 1], cx.L); pz = wrapg(cx.sp[3 * i + 2], cx.L);
+  }
+  bsum<4>(s, cx);
+  double vcm[3] = { s[0] * inv_mN, s[1] * inv_mN, s[2] * inv_mN };
+  double t[1] = { 0 };
+  if (own) { vx -= vcm[0]; vy -= vcm[1]; vz -= vcm[2]; t[0] += vx * vx + vy * vy + vz * vz; }
+  bsum<1>(t, cx);
+  const double tinst = m * t[0] / (3.0 * N - 3.0), fac = sqrt(t_target / tinst);
+  s[0] = s[1] = s[2] = s[3] = 0;
+  if (own) { vx *= fac; vy *= fac; vz *= fac; s[0] += m * vx; s[1] += m * vy; s[2] += m * vz; }
+  bsum<4>(s, cx);                                                   // 'velocity all zero linear'
+  vcm[0] = s[0] * inv_mN; vcm[1] = s[1] * inv_mN; vcm[2] = s[2] * inv_mN;
+  double xc[3] = { 0, 0, 0 };
+  if (own) { vx -= vcm[0]; vy -= vcm[1]; vz -= vcm[2]; xc[0] += m * px; xc[1] += m * py; xc[2] += m * pz; }
+  bsum<3>(xc, cx);                                                  // 'velocity all zero angular'
+  xc[0] *= inv_mN; xc[1] *= inv_mN; xc[2] *= inv_mN;
+  double a[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // L(3), Ixx Iyy Izz Ixy Iyz Ixz
+  const double dx = px - xc[0], dy = py - xc[1], dz = pz - xc[2];
+  if (own) {
+    a[0] += m * (dy * vz - dz * vy); a[1] += m * (dz * vx - dx * vz); a[2] += m * (dx * vy - dy * vx);
+    a[3] += m * (dy * dy + dz * dz); a[4] += m * (dx * dx + dz * dz); a[5] += m * (dx * dx + dy * dy);
+    a[6] -= m * dx * dy; a[7] -= m * dy * dz; a[8] -= m * dx * dz;
+  }
+  bsum<9>(a, cx);
+  const double I00 = a[3], I11 = a[4], I22 = a[5], I01 = a[6], I12 = a[7], I02 = a[8];
+  const double det = I00 * (I11 * I22 - I12 * I12) - I01 * (I01 * I22 - I12 * I02) + I02 * (I01 * I12 - I11 * I02);
+  double w0 = 0, w1 = 0, w2 = 0;
+  if (det > 0.0) {
+    const double id = 1.0 / det;
+    const double i00 = (I11 * I22 - I12 * I12) * id, i01 = -(I01 * I22 - I02 * I12) * id, i02 = (I01 * I12 - I02 * I11) * id;
+    const double i11 = (I00 * I22 - I02 * I02) * id, i12 = -(I00 * I12 - I02 * I01) * id, i22 = (I00 * I11 - I01 * I01) * id;
+    w0 = i00 * a[0] + i01 * a[1] + i02 * a[2];
+    w1 = i01 * a[0] + i11 * a[1] + i12 * a[2];
+    w2 = i02 * a[0] + i12 * a[1] + i22 * a[2];
+  }
+  t[0] = 0;
+  if (own) {
+    vx -= (w1 * dz - w2 * dy); vy -= (w2 * dx - w0 * dz); vz -= (w0 * dy - w1 * dx);
+    cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
+    t[0] += vx * vx + vy * vy + vz * vz;
+  }
+  bsum<1>(t, cx);
+  return 0.5 * m * t[0];
+}
+
 __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_target) {
+  if (cx.N <= (int)blockDim.x) return velocity_create_1(d, cx, r, t_target);
   const int N = cx.N, Npad = cx.Npad;
-  const double m = d.mass, inv = 1.0 / sqrt(m);
+  const double m = d.mass, inv = 1.0 / sqrt(m), inv_mN = 1.0 / (m * cx.N);
   double s[4] = { 0, 0, 0, 0 };
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     double g[3]; rng_gauss3(r, (uint32_t)i, P_HMC_VEL, g);
@@ -1069,15 +1146,15 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
     cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
     s[0] += m * vx; s[1] += m * vy; s[2] += m * vz;
   }
-  block_sum<4>(s, cx.red);
-  double vcm[3] = { s[0] / (m * N), s[1] / (m * N), s[2] / (m * N) };
+  bsum<4>(s, cx);
+  double vcm[3] = { s[0] * inv_mN, s[1] * inv_mN, s[2] * inv_mN };
   double t[1] = { 0 };
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const double vx = cx.gv[i] - vcm[0], vy = cx.gv[Npad + i] - vcm[1], vz = cx.gv[2 * Npad + i] - vcm[2];
     cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
     t[0] += vx * vx + vy * vy + vz * vz;
   }
-  block_sum<1>(t, cx.red);
+  bsum<1>(t, cx);
   const double tinst = m * t[0] / (3.0 * N - 3.0), fac = sqrt(t_target / tinst);
   s[0] = s[1] = s[2] = s[3] = 0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -1085,15 +1162,15 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
     cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
     s[0] += m * vx; s[1] += m * vy; s[2] += m * vz;
   }
-  block_sum<4>(s, cx.red);                                                   // 'velocity all zero linear'
-  vcm[0] = s[0] / (m * N); vcm[1] = s[1] / (m * N); vcm[2] = s[2] / (m * N);
+  bsum<4>(s, cx);                                                   // 'velocity all zero linear'
+  vcm[0] = s[0] * inv_mN; vcm[1] = s[1] * inv_mN; vcm[2] = s[2] * inv_mN;
   double xc[3] = { 0, 0, 0 };
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     cx.gv[i] -= vcm[0]; cx.gv[Npad + i] -= vcm[1]; cx.gv[2 * Npad + i] -= vcm[2];
     xc[0] += m * wrapg(cx.sp[3 * i], cx.L); xc[1] += m * wrapg(cx.sp[3 * i + 1], cx.L); xc[2] += m * wrapg(cx.sp[3 * i + 2], cx.L);
   }
-  block_sum<3>(xc, cx.red);                                                  // 'velocity all zero angular'
-  xc[0] /= (m * N); xc[1] /= (m * N); xc[2] /= (m * N);
+  bsum<3>(xc, cx);                                                  // 'velocity all zero angular'
+  xc[0] *= inv_mN; xc[1] *= inv_mN; xc[2] *= inv_mN;
   double a[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };   // L(3), Ixx Iyy Izz Ixy Iyz Ixz
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const double dx = wrapg(cx.sp[3 * i], cx.L) - xc[0], dy = wrapg(cx.sp[3 * i + 1], cx.L) - xc[1], dz = wrapg(cx.sp[3 * i + 2], cx.L) - xc[2];
@@ -1102,13 +1179,14 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
     a[3] += m * (dy * dy + dz * dz); a[4] += m * (dx * dx + dz * dz); a[5] += m * (dx * dx + dy * dy);
     a[6] -= m * dx * dy; a[7] -= m * dy * dz; a[8] -= m * dx * dz;
   }
-  block_sum<9>(a, cx.red);
+  bsum<9>(a, cx);
   const double I00 = a[3], I11 = a[4], I22 = a[5], I01 = a[6], I12 = a[7], I02 = a[8];
   const double det = I00 * (I11 * I22 - I12 * I12) - I01 * (I01 * I22 - I12 * I02) + I02 * (I01 * I12 - I11 * I02);
   double w0 = 0, w1 = 0, w2 = 0;
   if (det > 0.0) {
-    const double i00 = (I11 * I22 - I12 * I12) / det, i01 = -(I01 * I22 - I02 * I12) / det, i02 = (I01 * I12 - I02 * I11) / det;
-    const double i11 = (I00 * I22 - I02 * I02) / det, i12 = -(I00 * I12 - I02 * I01) / det, i22 = (I00 * I11 - I01 * I01) / det;
+    const double id = 1.0 / det;
+    const double i00 = (I11 * I22 - I12 * I12) * id, i01 = -(I01 * I22 - I02 * I12) * id, i02 = (I01 * I12 - I02 * I11) * id;
+    const double i11 = (I00 * I22 - I02 * I02) * id, i12 = -(I00 * I12 - I02 * I01) * id, i22 = (I00 * I11 - I01 * I01) * id;
     w0 = i00 * a[0] + i01 * a[1] + i02 * a[2];
     w1 = i01 * a[0] + i11 * a[1] + i12 * a[2];
     w2 = i02 * a[0] + i12 * a[1] + i22 * a[2];
@@ -1120,7 +1198,7 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
     cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
     t[0] += vx * vx + vy * vy + vz * vz;
   }
-  block_sum<1>(t, cx.red);
+  bsum<1>(t, cx);
   return 0.5 * m * t[0];
 }
 
@@ -1289,7 +1367,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
     const double vx = cx.gv[i], vy = cx.gv[cx.Npad + i], vz = cx.gv[2 * cx.Npad + i];
     t[0] += vx * vx + vy * vy + vz * vz;
   }
-  block_sum<1>(t, cx.red);
+  bsum<1>(t, cx);
   const int slot = d.cfg_slot[cx.c];
   if (f_out_aos) {
     double* fo = f_out_aos + (size_t)slot * 3 * cx.N;
@@ -1339,7 +1417,7 @@ k_cycle(Dev d, long long cycle) {
     const double vx = cx.gv[i], vy = cx.gv[Npad + i], vz = cx.gv[2 * Npad + i];
     t[0] += vx * vx + vy * vy + vz * vz;
   }
-  block_sum<1>(t, cx.red);
+  bsum<1>(t, cx);
   store_positions(cx);
   if (threadIdx.x == 0) {
     const double ke = 0.5 * d.mass * t[0], dof = 3.0 * N - 3.0, temp = 2.0 * ke / dof, vol = pow(cx.L, 3.0);
