@@ -661,56 +661,68 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
 // The owning thread streams its outer row (already ordered by image group, so the inner row inherits the grouping),
 // packs the surviving indices four at a time into one 64-bit register (stored XOR the dummy index, so that untouched
 // fields read as the dummy atom) and emits whole 8-byte quads into the [quad][atom] layout the force loop reads.
-__device__ void build_inner(const Dev& d, Ctx& cx) {
+// One pass over the owner's outer quads ([quad][atom] rows walked with byte pointers). Hits are pushed from the top
+// into a 128-bit shift register (predicated, no branch per candidate); once per outer quad the four oldest entries
+// are emitted as one 8-byte quad. Entries are stored XOR N so that the zero bits of a partial quad read as the dummy.
+template <bool MIC>
+__device__ void build_inner_t(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
-  __syncthreads();
-  wrap_and_refresh(cx, false);
-  __syncthreads();
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
-  const float magic = 12582912.f;
-  const bool mic = cx.mic;
   const unsigned long long dummy4 = 0x0001000100010001ull * (unsigned long long)N;
-  unsigned long long* l64 = reinterpret_cast<unsigned long long*>(cx.list);
+  const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf);
+  const unsigned rowbytes = (unsigned)Npad * 8u;
   double tot = 0.0; int over = 0;
   for (int i = tid; i < N; i += nthr) {
     const float4 pi = cx.sf[i];
     const int nqo = cx.onq[i];
-    const ushort4* orow = cx.olist + i;          // [quad][atom]: a warp reads 256 contiguous bytes per quad
-    const uint8_t* crow = cx.ocode + i;
-    unsigned long long acc = 0ull;
-    int oq = 0, fill = 0, curcode = 13, cnt = 0;
-    auto flush = [&]() {
+    const char* op = reinterpret_cast<const char*>(cx.olist + i);
+    const uint8_t* cp = cx.ocode + i;
+    char* lq = reinterpret_cast<char*>(cx.list + i);
+    unsigned long long hi = 0ull, lo = 0ull;
+    int oq = 0, fill = 0, cnt = 0;
+    unsigned curcode = 13u;
+    auto emit = [&](unsigned long long quad) {
       if (oq < d.maxq) {
-        const unsigned long long codebits = ((unsigned long long)(curcode & 7) << 13) | ((unsigned long long)(curcode >> 3) << 29);
-        l64[(size_t)oq * Npad + i] = (acc ^ dummy4) | codebits;
+        const unsigned long long codebits = ((unsigned long long)(curcode & 7u) << 13) | ((unsigned long long)(curcode >> 3) << 29);
+        *reinterpret_cast<unsigned long long*>(lq) = (quad ^ dummy4) | codebits;
+        lq += rowbytes;
       } else over = 1;
-      oq++; fill = 0; acc = 0ull;
+      oq++;
     };
-    ushort4 e4 = nqo > 0 ? orow[0] : make_ushort4(0, 0, 0, 0);
-    int code = nqo > 0 ? crow[0] : 13;
+    uint2 e = *reinterpret_cast<const uint2*>(op);
+    unsigned code = *cp;
     for (int q = 0; q < nqo; q++) {
-      const ushort4 n4 = (q + 1 < nqo) ? orow[(size_t)(q + 1) * Npad] : e4;
-      const int ncode = (q + 1 < nqo) ? crow[(size_t)(q + 1) * Npad] : 13;
-      if (code != curcode) { if (fill) flush(); curcode = code; }
-      const float sx = (float)(code / 9 - 1), sy = (float)((code / 3) % 3 - 1), sz = (float)(code % 3 - 1);
-      const int jj[4] = { e4.x, e4.y, e4.z, e4.w };
+      op += rowbytes; cp += Npad;
+      const uint2 en = *reinterpret_cast<const uint2*>(op);      // rows past nqo are allocated and never used
+      const unsigned coden = *cp;
+      if (code != curcode) {                                     // new image group: close the partial quad
+        if (fill) { emit(hi >> (64 - 16 * fill)); fill = 0; }
+        curcode = code;
+      }
+      float px = pi.x, py = pi.y, pz = pi.z;
+      if (!MIC) { px -= (float)((int)(code / 9u) - 1); py -= (float)((int)((code / 3u) % 3u) - 1); pz -= (float)((int)(code % 3u) - 1); }
+      const unsigned jj[4] = { e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16 };
 #pragma unroll
       for (int t = 0; t < 4; t++) {
-        const float4 pj = cx.sf[jj[t]];
-        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-        if (mic) { dx -= __fadd_rn(__fadd_rn(dx, magic), -magic); dy -= __fadd_rn(__fadd_rn(dy, magic), -magic); dz -= __fadd_rn(__fadd_rn(dz, magic), -magic); }
-        else { dx -= sx; dy -= sy; dz -= sz; }
-        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (r2 < rl2f) {
-          acc |= (unsigned long long)(jj[t] ^ N) << (16 * fill);
-          cnt++;
-          if (++fill == 4) flush();
+        float4 pj;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(pj.w) : "r"(sf_s + 16u * jj[t]));
+        float dx = px - pj.x, dy = py - pj.y, dz = pz - pj.z;
+        if (MIC) { dx = fabsf(dx); dy = fabsf(dy); dz = fabsf(dz); dx = fminf(dx, 1.f - dx); dy = fminf(dy, 1.f - dy); dz = fminf(dz, 1.f - dz); }
+        if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) < rl2f) {        // predicated push from the top
+          lo = (lo >> 16) | (hi << 48);
+          hi = (hi >> 16) | ((unsigned long long)(jj[t] ^ (unsigned)N) << 48);
+          fill++; cnt++;
         }
       }
-      e4 = n4; code = ncode;
+      if (fill >= 4) {                                           // the four oldest entries start 16*fill bits from the top
+        const int sh = 16 * fill - 64;                           // 0, 16, 32 or 48
+        emit(sh ? (hi << sh) | (lo >> (64 - sh)) : hi);
+        fill -= 4;
+      }
+      e = en; code = coden;
     }
-    if (fill) flush();
+    if (fill) emit(hi >> (64 - 16 * fill));
     cx.nnb[i] = (uint16_t)min(oq, d.maxq);
     tot += cnt;
     cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
@@ -721,6 +733,12 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
   if (r[1] > 0.0) cx.status |= ST_NEIGH;
   cx.L0 = L;
   update_thr(d, cx);
+}
+__device__ void build_inner(const Dev& d, Ctx& cx) {
+  __syncthreads();
+  wrap_and_refresh(cx, false);
+  __syncthreads();
+  if (cx.mic) build_inner_t<true>(d, cx); else build_inner_t<false>(d, cx);
 }
 
 // (re)build: make sure the outer list can still supply every pair within rl, then regenerate the inner list
@@ -1676,7 +1694,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, per);
   DA(d.list, ((size_t)nrep * d.maxq + 2) * d.Npad); DA(d.qcode, (size_t)nrep * d.maxq * d.Npad);
   DA(d.ltmp, (size_t)nrep * ((d.maxnbo + 3) & ~3) * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad); DA(d.micmode, nrep);
-  DA(d.olist, (size_t)nrep * d.maxqo * d.Npad); DA(d.ocode, (size_t)nrep * d.maxqo * d.Npad); DA(d.onq, (size_t)nrep * d.Npad);
+  DA(d.olist, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.ocode, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.onq, (size_t)nrep * d.Npad);
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
