@@ -448,6 +448,30 @@ def test_small_box_minimum_image_path(nm, orc):
         np.testing.assert_allclose(th[k, :9], th_o[:9], rtol=2e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("skin", [0.05, 0.15, 0.22, 0.24, 0.3, 0.6, 0.68])
+def test_list_build_paths_across_box_to_list_ratio(nm, orc, skin):
+    """r_list/L from 0.40 to 0.50 at N = 256: image groups from the 16-bin masks (< 0.43), the per-hit classification
+    (0.43 .. 0.5) and the per-pair minimum image (>= 0.5) must all reproduce the oracle"""
+    x, box = _configs(orc, 4, [1.0, 0.97], [0.05, 0.07], seed=91)          # L = 6.35, 6.41
+    box = np.array([orc.round6(b) for b in box])
+    with nm.Engine(natoms=256, n_rep=2, nt=2, skin=skin, mod=8, bulk_move=True, seed=11) as eng:
+        eng.set_labels([0.7, 1.4], [4.0 / 0.7, 4.0 / 1.4], [0.7, 1.4])
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[.03, .03], dv=[.03, .03], dt=[.004, .004])
+        pe, w, f, npairs = eng.eval()
+        for k in range(2):
+            pe_o, w_o, f_o, np_o = orc.lj_eval_list(x[k], box[k])
+            assert npairs[k] == np_o and abs(pe[k] - pe_o) <= 1e-10 * abs(pe_o) and abs(w[k] - w_o) <= 1e-10 * abs(w_o)
+            assert np.abs(f[k] - f_o).max() <= 1e-10 * np.abs(f_o).max()
+        eng.run_cycle(0)
+        th = eng.get_thermo()
+    params = orc.make_params(mod=8, bulk_move=1, seed=11)
+    for k, T in enumerate((0.7, 1.4)):
+        xo, vo = x[k].copy(), np.zeros(768)
+        th_o, _ = orc.cycle(params, [T, 4.0 / T, T, orc.round6(T)], k, 0, xo, vo, np.array([box[k], .03, .03, .004]), np.zeros(6))
+        np.testing.assert_array_equal(th[k, 9:], th_o[9:])
+        np.testing.assert_allclose(th[k, :9], th_o[:9], rtol=2e-9, atol=1e-9)
+
+
 # ------------------------------------------------------------------ size-independent properties at the BASELINE sizes
 @pytest.mark.parametrize("n_side", [5, 10])
 def test_eval_invariances_at_full_size(nm, orc, n_side):
