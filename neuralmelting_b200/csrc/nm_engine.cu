@@ -56,6 +56,7 @@ struct Dev {
   int *cfg_slot, *slot_cfg;                // local permutation
   unsigned long long* cta_clk;             // [nrep] SM clocks the configuration's CTA spent in the last cycle
   unsigned long long* rep_ct;              // [nrep][NM_COUNTER_WIDTH] the last cycle's counters of each configuration
+  unsigned long long* mv_clk;              // [nrep][4] last cycle: SM clocks in PMC / VMC / HMC moves (solo-corrected), [3] = moves of each kind packed 3 x 16 bit
   int* order;                              // [nrep] blockIdx -> configuration (cost-balanced placement)
   int *status;                             // [nrep]
   // per local slot
@@ -75,6 +76,7 @@ struct Ctx {
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
   uint16_t *cell_atoms, *atom_cell;
+  uint16_t* gcur;               // shared (LARGE mode): [8][nthr] per-thread group counters / cursors of the outer build
   uint2* gtab;                  // shared (SMALL mode): [8][nthr] per-thread {cursor, image-code bits} of the 8 image groups
   unsigned long long* s_pairs;  // shared: in-cutoff ordered pairs of force-only evaluations
   // global views of this configuration
@@ -99,6 +101,7 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
   b += sizeof(unsigned long long) * 2;
   b += sizeof(uint16_t) * 2 * (size_t)Npad;
   if (small) b += sizeof(uint32_t) * (hbits_words(N) + (hbits_words(N) & 1)) + sizeof(uint2) * 8 * (size_t)nthr;
+  else b += sizeof(uint16_t) * 8 * (size_t)nthr;          // outer build: per-thread group counters / cursors
   return b;
 }
 
@@ -127,12 +130,13 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.cell_atoms = h; cx.atom_cell = h + d.Npad;
   cx.hbits = reinterpret_cast<uint32_t*>(h + 2 * d.Npad);
   cx.gtab = reinterpret_cast<uint2*>(cx.hbits + hbits_words(d.N) + (hbits_words(d.N) & 1));   // SMALL mode only
+  cx.gcur = reinterpret_cast<uint16_t*>(cx.hbits);                                           // LARGE mode only (no hit matrix there)
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
   cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off; cx.gx0 = d.x0 + off;
   cx.list = d.list + (size_t)c * d.maxq * d.Npad;
   cx.qcode = d.qcode + (size_t)c * d.maxq * d.Npad;
-  cx.ltmp = d.ltmp + (size_t)c * ((d.maxnbo + 3) & ~3) * d.Npad;
+  cx.ltmp = d.ltmp + (size_t)c * ((d.maxnbo + 3) & ~3) * d.Npad;     // [entry][atom]
   cx.olist = d.olist + (size_t)c * d.maxqo * d.Npad;
   cx.ocode = d.ocode + (size_t)c * d.maxqo * d.Npad;
   cx.onq = d.onq + (size_t)c * d.Npad;
@@ -204,122 +208,95 @@ __device__ __forceinline__ ushort4 pack_code(ushort4 v, int code) {
 // once per non-empty group and emits whole quads (8 bytes).
 // Candidates: all atoms (nc == 1), the 27 stencil cells (nc >= 3), or -- BITS -- the set bits of the atom's row in the
 // shared-memory hit matrix. Output: OUTER rows (row-major per atom) or, BITS mode, the [quad][atom] force-loop layout.
-template <bool BITS>
-__device__ int grouped_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
+__device__ int outer_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double invL = 1.0 / cx.L;
-  const float magic = 12582912.f;          // 1.5 * 2^23: (x + magic) - magic = rint(x) for |x| < 2^22
   const bool grouped = !cx.mic;
-  const int trow_len = (d.maxnbo + 3) & ~3, capq = BITS ? d.maxq : d.maxqo;
-  const int W = (N + 31) / 32;
+  const int capq = d.maxqo, maxnbo = d.maxnbo;
+  const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf);
+  const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cx.gcur + tid), gstep = 2u * (unsigned)nthr;
+  uint16_t* ol16 = reinterpret_cast<uint16_t*>(cx.olist);
   int over = 0;
-  double tot = 0.0;
   for (int i = tid; i < N; i += nthr) {
     const float4 pi = cx.sf[i];
-    uint32_t* trow = cx.ltmp + (size_t)i * trow_len;
-    unsigned long long gcnt_lo = 0ull, gcnt_hi = 0ull;   // 8 image-group counters, 16 bits each
+    uint32_t* trow = cx.ltmp + i;                          // scratch entry t of atom i: trow[t * Npad] (coalesced over atoms)
+#pragma unroll
+    for (int g = 0; g < 8; g++) asm volatile("st.shared.u16 [%0], %1;" :: "r"(cur_s + g * gstep), "h"((unsigned short)0) : "memory");
     int cnt = 0;
-    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    // pass A: candidates in a fixed order (stencil cell by stencil cell, ascending index inside a cell); hits go to the
+    // scratch column with their image group, group sizes to the shared counters
     auto test = [&](int j) {
-      const float4 pj = cx.sf[j];
-      float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      const float kx = __fadd_rn(__fadd_rn(dx, magic), -magic), ky = __fadd_rn(__fadd_rn(dy, magic), -magic),
-                  kz = __fadd_rn(__fadd_rn(dz, magic), -magic);
-      dx -= kx; dy -= ky; dz -= kz;
-      const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      if (BITS || (r2 < rl2f && j != i)) {
-        if (cnt < d.maxnbo) {
-          const int g = grouped ? ((kx != 0.f) | ((ky != 0.f) << 1) | ((kz != 0.f) << 2)) : 0;
-          const uint32_t en = (uint32_t)j | ((uint32_t)g << 16);
-          const int slot = cnt & 3;
-          if (!BITS) {
-            b0 = slot == 0 ? en : b0; b1 = slot == 1 ? en : b1; b2 = slot == 2 ? en : b2; b3 = slot == 3 ? en : b3;
-            if (slot == 3) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
-          }
-          if (g < 4) gcnt_lo += 1ull << (16 * g); else gcnt_hi += 1ull << (16 * (g - 4));
+      float4 pj;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(pj.w) : "r"(sf_s + 16u * (unsigned)j));
+      const float ax = fabsf(pi.x - pj.x), ay = fabsf(pi.y - pj.y), az = fabsf(pi.z - pj.z);
+      const float mx = fminf(ax, 1.f - ax), my = fminf(ay, 1.f - ay), mz = fminf(az, 1.f - az);
+      if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < rl2f && j != i) {
+        if (cnt < maxnbo) {
+          const unsigned g = grouped ? ((ax > 0.5f) | ((ay > 0.5f) << 1) | ((az > 0.5f) << 2)) : 0u;
+          trow[(size_t)cnt * Npad] = (uint32_t)j | (g << 16);
+          const unsigned ca = cur_s + g * gstep;
+          unsigned short c16;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c16) : "r"(ca));
+          asm volatile("st.shared.u16 [%0], %1;" :: "r"(ca), "h"((unsigned short)(c16 + 1)) : "memory");
         }
         cnt++;
       }
     };
-    if (BITS) {
-      const uint32_t* row = cx.hbits + (size_t)i * (W | 1);
-      for (int w = 0; w < W; w++) {
-        uint32_t m = row[w];
-        while (m) { const int b = __ffs(m) - 1; m &= m - 1; test(w * 32 + b); }
-      }
-    } else if (nc == 1) {
+    if (nc == 1) {
       for (int j = 0; j < N; j++) test(j);
     } else {
       const int ci = cx.atom_cell[i], a = ci / (nc * nc), b = (ci / nc) % nc, e = ci % nc;
-      for (int da = -sw; da <= sw; da++) for (int db = -sw; db <= sw; db++) for (int de = -sw; de <= sw; de++) {
-        const int cc = (((a + da + nc) % nc) * nc + (b + db + nc) % nc) * nc + (e + de + nc) % nc;
-        const int s = cx.cell_start[cc], en = cx.cell_start[cc + 1];
-        for (int p = s; p < en; p++) test(cx.cell_atoms[p]);
+      // the stencil cells along the fastest axis are contiguous in the cell order: one or (across the boundary) two
+      // ranges per (da, db) instead of 2 sw + 1 cells
+      int lo1 = e - sw, hi1 = e + sw, lo2 = 0, hi2 = -1;
+      if (lo1 < 0) { lo2 = 0; hi2 = hi1; hi1 = nc - 1; lo1 += nc; }
+      else if (hi1 >= nc) { lo2 = 0; hi2 = hi1 - nc; hi1 = nc - 1; }
+      for (int da = -sw; da <= sw; da++) {
+        const int am = (a + da + nc) % nc;
+        for (int db = -sw; db <= sw; db++) {
+          const int rowc = (am * nc + (b + db + nc) % nc) * nc;
+          for (int p = cx.cell_start[rowc + lo1], en = cx.cell_start[rowc + hi1 + 1]; p < en; p++) test(cx.cell_atoms[p]);
+          if (hi2 >= 0) for (int p = cx.cell_start[rowc + lo2], en = cx.cell_start[rowc + hi2 + 1]; p < en; p++) test(cx.cell_atoms[p]);
+        }
       }
     }
-    if (cnt > d.maxnbo) { over = 1; cnt = d.maxnbo; }
-    if (!BITS && (cnt & 3)) *reinterpret_cast<uint4*>(trow + (cnt & ~3)) = make_uint4(b0, b1, b2, b3);
+    if (cnt > maxnbo) { over = 1; cnt = maxnbo; }
+    // group sizes -> start cursors (quad-padded), image codes
     const int sx = pi.x < 0.5f ? -1 : 1, sy = pi.y < 0.5f ? -1 : 1, sz = pi.z < 0.5f ? -1 : 1;
-    int q = 0;
-    auto emit = [&](ushort4 v, int code) {
-      if (BITS) cx.list[(size_t)q * Npad + i] = pack_code(v, code);
-      else { cx.olist[(size_t)q * Npad + i] = v; cx.ocode[(size_t)q * Npad + i] = (uint8_t)code; }
-      q++;
-    };
-    for (int g = 0; g < 8; g++) {
-      const int ng = (int)(((g < 4 ? gcnt_lo >> (16 * g) : gcnt_hi >> (16 * (g - 4)))) & 0xffffull);
-      if (ng == 0) continue;
-      if (q + ((ng + 3) >> 2) > capq) { over = 1; break; }
-      const int code = 13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz;
-      unsigned short a0 = (unsigned short)N, a1 = a0, a2 = a0, a3 = a0;
-      int fill = 0;
-      auto take = [&](unsigned short j) {
-        a0 = fill == 0 ? j : a0; a1 = fill == 1 ? j : a1; a2 = fill == 2 ? j : a2; a3 = fill == 3 ? j : a3;
-        if (++fill == 4) { emit(make_ushort4(a0, a1, a2, a3), code); fill = 0; a0 = a1 = a2 = a3 = (unsigned short)N; }
-      };
-      if (BITS) {
-        // re-walk the atom's bit row (shared memory) and recompute the image group of each hit: no global scratch
-        const uint32_t* row = cx.hbits + (size_t)i * (W | 1);
-        for (int w = 0; w < W; w++) {
-          uint32_t m = row[w];
-          while (m) {
-            const int j = w * 32 + __ffs(m) - 1; m &= m - 1;
-            int gj = 0;
-            if (grouped) {
-              const float4 pj = cx.sf[j];
-              const float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-              gj = (__fadd_rn(__fadd_rn(dx, magic), -magic) != 0.f) | ((__fadd_rn(__fadd_rn(dy, magic), -magic) != 0.f) << 1) |
-                   ((__fadd_rn(__fadd_rn(dz, magic), -magic) != 0.f) << 2);
-            }
-            if (gj == g) take((unsigned short)j);
-          }
-        }
-      } else {
-        uint4 e4 = *reinterpret_cast<const uint4*>(trow);
-        for (int t = 0; t < cnt; t += 4) {
-          const uint4 n4 = (t + 4 < cnt) ? *reinterpret_cast<const uint4*>(trow + t + 4) : e4;
-          const uint32_t ee[4] = { e4.x, e4.y, e4.z, e4.w };
-          e4 = n4;
+    int ng[8], run = 0;
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-            if (t + u < cnt && (int)(ee[u] >> 16) == g) take((unsigned short)(ee[u] & 0xffffu));
-        }
-      }
-      if (fill) emit(make_ushort4(a0, a1, a2, a3), code);
+    for (int g = 0; g < 8; g++) {
+      unsigned short c16;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(c16) : "r"(cur_s + g * gstep));
+      ng[g] = c16;
+      asm volatile("st.shared.u16 [%0], %1;" :: "r"(cur_s + g * gstep), "h"((unsigned short)run) : "memory");
+      run += (ng[g] + 3) & ~3;
     }
-    if (BITS) {
-      cx.nnb[i] = (uint16_t)q;
-      cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
-      tot += cnt;
-    } else {
-      cx.onq[i] = (uint16_t)q;
-      cx.gx0o[i] = cx.sp[3 * i] * invL; cx.gx0o[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0o[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+    const int nq = run >> 2;
+    if (nq > capq) { over = 1; cx.onq[i] = 0; continue; }
+    uint16_t* oi = ol16 + (size_t)i * 4;
+    const unsigned qstride = (unsigned)Npad * 4u;
+    // pass B: one sweep over the scratch column, every index straight to its slot of the [quad][atom] layout
+    for (int t = 0; t < cnt; t++) {
+      const uint32_t en = trow[(size_t)t * Npad];
+      const unsigned ca = cur_s + (en >> 16) * gstep;
+      unsigned short pos;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pos) : "r"(ca));
+      asm volatile("st.shared.u16 [%0], %1;" :: "r"(ca), "h"((unsigned short)(pos + 1)) : "memory");
+      oi[(pos >> 2) * qstride + (pos & 3)] = (uint16_t)(en & 0xffffu);
     }
-  }
-  if (BITS) {
-    double r[1] = { tot };
-    bsum<1>(r, cx);
-    cx.list_pairs = 0.5 * r[0];
+    int q0 = 0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+      if (ng[g] == 0) continue;
+      const int code = 13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz;
+      for (unsigned pos = (unsigned)(4 * q0 + ng[g]); pos & 3u; pos++) oi[(pos >> 2) * qstride + (pos & 3u)] = (uint16_t)N;   // dummy padding
+      const int nqg = (ng[g] + 3) >> 2;
+      for (int q = q0; q < q0 + nqg; q++) cx.ocode[(size_t)q * Npad + i] = (uint8_t)code;
+      q0 += nqg;
+    }
+    cx.onq[i] = (uint16_t)nq;
+    cx.gx0o[i] = cx.sp[3 * i] * invL; cx.gx0o[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0o[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
   }
   return over;
 }
@@ -650,7 +627,7 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
     __syncthreads();
   }
   const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
-  const int over = grouped_rows<false>(d, cx, rl2f, nc, sw);
+  const int over = outer_rows(d, cx, rl2f, nc, sw);
   if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
   cx.L0o = L;
   update_thr(d, cx);
@@ -1419,15 +1396,18 @@ k_cycle(Dev d, long long cycle) {
   double cnt[6];
   for (int k = 0; k < 6; k++) cnt[k] = d.cnt[6 * c + k];
   __syncthreads();
+  unsigned long long kclk[3] = { 0ull, 0ull, 0ull }; unsigned kcnt[3] = { 0u, 0u, 0u };   // per move kind (thread 0)
   for (int mv = 0; mv < d.mod; mv++) {
     const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)(d.rep_offset + slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
     const double roll = rng_uniform(r, 0, P_ROLL);
-    if (roll <= d.ppos) {
+    const long long t_mv0 = clock64();
+    const int kind = roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2);
+    if (kind == 0) {
       if (d.bulk) bulk_position_mc(d, cx, r, et, dxs, en, cnt);
       else iter_position_mc(d, cx, r, et, dxs, en, cnt);
-    } else if (roll <= (d.ppos + d.pvol)) volume_mc(d, cx, r, et, pf, dvs, en, cnt);
+    } else if (kind == 1) volume_mc(d, cx, r, et, pf, dvs, en, cnt);
     else hamiltonian_mc(d, cx, r, et, t_vel, dts, en, cnt);
-    if (threadIdx.x == 0) cx.ct[NM_CT_SWEEPS]++;
+    if (threadIdx.x == 0) { cx.ct[NM_CT_SWEEPS]++; kclk[kind] += (unsigned long long)(clock64() - t_mv0); kcnt[kind]++; }
   }
   // lammps_extract
   double t[1] = { 0 };
@@ -1456,6 +1436,8 @@ k_cycle(Dev d, long long cycle) {
     // placement cost: a CTA that had its SM to itself ran ~1.4x faster than it would have next to a neighbour (measured)
     const bool solo = d.per_sm == 2 && d.nrep > d.nsm && d.nrep <= 2 * d.nsm && (int)blockIdx.x >= d.nrep - d.nsm && (int)blockIdx.x < d.nsm;
     d.cta_clk[c] = solo ? dt_cycle + dt_cycle * 2 / 5 : dt_cycle;
+    for (int k = 0; k < 3; k++) d.mv_clk[4 * c + k] = solo ? kclk[k] + kclk[k] * 2 / 5 : kclk[k];
+    d.mv_clk[4 * c + 3] = (unsigned long long)min(kcnt[0], 65535u) | ((unsigned long long)min(kcnt[1], 65535u) << 16) | ((unsigned long long)min(kcnt[2], 65535u) << 32);
     for (int k = 0; k < NM_COUNTER_WIDTH; k++) { d.rep_ct[(size_t)c * NM_COUNTER_WIDTH + k] = cx.ct[k]; if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]); }
   }
 }
@@ -1464,10 +1446,32 @@ k_cycle(Dev d, long long cycle) {
 // nrep <= 2 nsm (the block scheduler fills SMs round-robin). With last cycle's per-configuration clocks sorted in
 // descending order, the nsm-(nrep-nsm) SMs that hold a single CTA get the most expensive configurations and every
 // other SM pairs an expensive with a cheap one. Larger grids are launched in descending cost (longest first).
-__global__ void k_schedule(Dev d, int nsm, int per_sm) {
+__global__ void k_schedule(Dev d, int nsm, int per_sm, long long cycle) {
   extern __shared__ unsigned long long sclk[];
   int* sorted = reinterpret_cast<int*>(sclk + d.nrep);
-  for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) sclk[c] = d.cta_clk[c];
+  // predicted cost of the coming cycle: the move kinds are known in advance (counter-based RNG: the same rolls
+  // k_cycle will draw), the cost of a move of each kind is last cycle's average for this configuration
+  for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) {
+    const unsigned long long packed = d.mv_clk[4 * c + 3], total = d.cta_clk[c];
+    const unsigned last[3] = { (unsigned)(packed & 0xffffull), (unsigned)((packed >> 16) & 0xffffull), (unsigned)((packed >> 32) & 0xffffull) };
+    const unsigned nlast = last[0] + last[1] + last[2];
+    unsigned long long cost = total;
+    if (nlast) {
+      unsigned n[3] = { 0u, 0u, 0u };
+      const int slot = d.cfg_slot[c];
+      for (int mv = 0; mv < d.mod; mv++) {
+        const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)(d.rep_offset + slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
+        const double roll = rng_uniform(r, 0, P_ROLL);
+        n[roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2)]++;
+      }
+      cost = 0ull;
+      for (int k = 0; k < 3; k++) {
+        const unsigned long long per = last[k] ? d.mv_clk[4 * c + k] / last[k] : total / nlast;   // kind not seen last cycle: the mean move
+        cost += per * n[k];
+      }
+    }
+    sclk[c] = cost;
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) {
     const unsigned long long v = sclk[c];
@@ -1698,7 +1702,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
-  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.order, nrep);
+  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep);
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
@@ -1839,16 +1843,16 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   if (!h) return fail(NM_EINVAL, "null engine");
   if (!h->have_state || !h->have_labels) return fail(NM_ESTATE, "nm_run_cycle: state and labels must be uploaded first");
   CK(cudaSetDevice(h->cfg.device));
+  if (h->d.nrep > h->nsm && h->d.nrep <= 4096) {        // placement from the last cycle's clocks and this cycle's move kinds
+    k_schedule<<<1, 1024, h->d.nrep * (sizeof(unsigned long long) + sizeof(int)), h->stream>>>(h->d, h->nsm, h->d.per_sm, (long long)cycle);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
   if (h->threads == 256) k_cycle<256><<<h->d.nrep, 256, h->smem, h->stream>>>(h->d, (long long)cycle);
   else if (h->threads == 512) k_cycle<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, (long long)cycle);
   else k_cycle<1024><<<h->d.nrep, 1024, h->smem, h->stream>>>(h->d, (long long)cycle);
   h->launches++;
   CK(cudaGetLastError());
-  if (h->d.nrep > h->nsm && h->d.nrep <= 4096) {        // placement for the next cycle from this cycle's clocks
-    k_schedule<<<1, 1024, h->d.nrep * (sizeof(unsigned long long) + sizeof(int)), h->stream>>>(h->d, h->nsm, h->d.per_sm);
-    h->launches++;
-    CK(cudaGetLastError());
-  }
   h->have_thermo = true;
   return NM_OK;
 }

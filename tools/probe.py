@@ -61,6 +61,8 @@ def main():
         r = rc[k]
         print("%4d  %.2f  %.3f  %5.1f  %4d %4d  %4d  %5d   %6.1f  %6.1f   %7.0f" % (k, tt[k], n / th[k, 5], r[ci["clk_total"]] / 1e6, r[ci["sweeps"]], r[ci["hmc_moves"]],
               r[ci["list_builds"]], r[ci["force_evals"]], r[ci["clk_build"]] / 1e6, r[ci["clk_eval"]] / 1e6, r[ci["list_pairs"]] / max(1, r[ci["force_evals"]])))
+    ctot = np.sort(rc[:, ci["clk_total"]] / 1e6)[::-1]
+    print("sorted clk_total (Mclk) deciles:", np.round(ctot[::max(1, len(ctot) // 16)], 1), " kernel %.1f Mclk at 1.965 GHz; sum/148 = %.1f" % (dt * 1965e6 / 1e6, ctot.sum() / 148))
     print("T col0 thermo:", np.round(th[:nt, :6], 3)[::max(1, nt // 4)])
 
 main()
