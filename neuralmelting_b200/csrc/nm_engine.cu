@@ -20,8 +20,9 @@
 
 namespace nm {
 
-constexpr int NCMAX = 12;                // cell grid is at most 12^3
-constexpr int RED_HALF = 32 * 12;          // one block_sum scratch area (K <= 12)
+constexpr int NCMAX = 10;                // cell grid is at most 10^3 (N = 4000 must stay below the 196 KB shared-memory carve-out: L1 keeps 60 KB)
+constexpr int RED_HALF = 32 * 9;           // one block_sum scratch area (K <= 9)
+static_assert(3 * 16 * 25 <= 2 * (NCMAX * NCMAX * NCMAX + 1), "bin masks of the SMALL builds live in the idle cell arrays");
 constexpr int RED_DOUBLES = 2 * RED_HALF;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
@@ -75,9 +76,9 @@ struct Ctx {
   uint32_t* hbits;              // shared (small mode): N x N hit bit matrix, row i = atoms within the list radius of i
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
-  uint16_t *cell_atoms, *atom_cell;
+  uint16_t* cell_atoms;
   uint16_t* gcur;               // shared (LARGE mode): [8][nthr] per-thread group counters / cursors of the outer build
-  uint2* gtab;                  // shared (SMALL mode): [8][nthr] per-thread {cursor, image-code bits} of the 8 image groups
+  uint16_t* gtab;               // shared (SMALL mode): [8][nthr] per-thread cursors of the 8 image groups
   unsigned long long* s_pairs;  // shared: in-cutoff ordered pairs of force-only evaluations
   // global views of this configuration
   double *gx, *gv, *gf, *gxs, *gvs, *gfs, *gx0;
@@ -99,8 +100,8 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
   b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8 + 2);   // +2: keeps the float4 block 16-byte aligned
   b += sizeof(float4) * (size_t)Npad;
   b += sizeof(unsigned long long) * 2;
-  b += sizeof(uint16_t) * 2 * (size_t)Npad;
-  if (small) b += sizeof(uint32_t) * (hbits_words(N) + (hbits_words(N) & 1)) + sizeof(uint2) * 8 * (size_t)nthr;
+  b += sizeof(uint16_t) * (size_t)Npad;
+  if (small) b += sizeof(uint32_t) * hbits_words(N) + sizeof(uint16_t) * 8 * (size_t)nthr;   // two 512-thread CTAs stay under the 164 KB carve-out
   else b += sizeof(uint16_t) * 8 * (size_t)nthr;          // outer build: per-thread group counters / cursors
   return b;
 }
@@ -108,6 +109,7 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
 // block_sum on alternating scratch halves (see nm_device.cuh): one barrier per reduction
 template <int K>
 __device__ __forceinline__ void bsum(double (&v)[K], Ctx& cx) {
+  static_assert(32 * K <= RED_HALF, "block_sum scratch");
   cx.redflip ^= 1;
   block_sum<K>(v, cx.red + cx.redflip * RED_HALF);
 }
@@ -127,9 +129,9 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.ibc = q; q += 8 + 2;
   cx.sf = reinterpret_cast<float4*>(q); q += 4 * d.Npad;
   uint16_t* h = reinterpret_cast<uint16_t*>(q);
-  cx.cell_atoms = h; cx.atom_cell = h + d.Npad;
-  cx.hbits = reinterpret_cast<uint32_t*>(h + 2 * d.Npad);
-  cx.gtab = reinterpret_cast<uint2*>(cx.hbits + hbits_words(d.N) + (hbits_words(d.N) & 1));   // SMALL mode only
+  cx.cell_atoms = h;
+  cx.hbits = reinterpret_cast<uint32_t*>(h + d.Npad);
+  cx.gtab = reinterpret_cast<uint16_t*>(cx.hbits + hbits_words(d.N));                        // SMALL mode only
   cx.gcur = reinterpret_cast<uint16_t*>(cx.hbits);                                           // LARGE mode only (no hit matrix there)
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
@@ -208,6 +210,10 @@ __device__ __forceinline__ ushort4 pack_code(ushort4 v, int code) {
 // once per non-empty group and emits whole quads (8 bytes).
 // Candidates: all atoms (nc == 1), the 27 stencil cells (nc >= 3), or -- BITS -- the set bits of the atom's row in the
 // shared-memory hit matrix. Output: OUTER rows (row-major per atom) or, BITS mode, the [quad][atom] force-loop layout.
+__device__ __forceinline__ int cell_of(const float4 p, int nc) {
+  const int a = min(nc - 1, (int)(p.x * nc)), b = min(nc - 1, (int)(p.y * nc)), e = min(nc - 1, (int)(p.z * nc));
+  return (a * nc + b) * nc + e;
+}
 __device__ int outer_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double invL = 1.0 / cx.L;
@@ -245,7 +251,7 @@ __device__ int outer_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
     if (nc == 1) {
       for (int j = 0; j < N; j++) test(j);
     } else {
-      const int ci = cx.atom_cell[i], a = ci / (nc * nc), b = (ci / nc) % nc, e = ci % nc;
+      const int ci = cell_of(pi, nc), a = ci / (nc * nc), b = (ci / nc) % nc, e = ci % nc;
       // the stencil cells along the fastest axis are contiguous in the cell order: one or (across the boundary) two
       // ranges per (da, db) instead of 2 sw + 1 cells
       int lo1 = e - sw, hi1 = e + sw, lo2 = 0, hi2 = -1;
@@ -424,7 +430,7 @@ __device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
   const double invL = 1.0 / cx.L;
   const uint32_t* M = reinterpret_cast<const uint32_t*>(cx.cell_cnt);
   uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
-  uint2* tab = cx.gtab + threadIdx.x;                      // entry of group g: tab[g * nthr]
+  uint16_t* tab = cx.gtab + threadIdx.x;                   // cursor of group g: tab[g * nthr]
   int over = 0; double tot = 0.0;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const float4 pi = cx.sf[i];
@@ -441,25 +447,22 @@ __device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
                         nZ - nXZ - nYZ + nXYZ, nXZ - nXYZ, nYZ - nXYZ, nXYZ };
     // image code of group g: -1 along an axis for atoms in the lower half of the box, +1 in the upper half
     const int sx = bx < 8 ? -1 : 1, sy = by < 8 ? -1 : 1, sz = bz < 8 ? -1 : 1;
+    const int cA = 9 * sx, cB = 3 * sy, cC = sz;           // code of group g = 13 + (g&1) cA + (g>>1&1) cB + (g>>2&1) cC
     int run = 0;
 #pragma unroll
-    for (int g = 0; g < 8; g++) {
-      const int code = 13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz;
-      tab[g * nthr] = make_uint2((unsigned)run, (unsigned)((code & 7) << 13) | ((unsigned)((code >> 3) << 13) << 16));
-      run += (cg[g] + 3) & ~3;
-    }
+    for (int g = 0; g < 8; g++) { tab[g * nthr] = (uint16_t)run; run += (cg[g] + 3) & ~3; }
     const int nq = run >> 2;
     if (nq > d.maxq) { over = 1; cx.nnb[i] = 0; continue; }
     // pass 2 runs on explicit 32-bit shared addresses (no generic-pointer arithmetic inside the loop)
     char* li = reinterpret_cast<char*>(l16 + (size_t)i * 4);
     asm volatile("" : "+l"(li));                            // keep the row base in registers (ptxas rematerialises it per store)
-    const unsigned rowbytes = (unsigned)Npad * 8u, gbytes = (unsigned)nthr * 8u;
+    const unsigned rowbytes = (unsigned)Npad * 8u, gbytes = (unsigned)nthr * 2u;
     const unsigned row_s = (unsigned)__cvta_generic_to_shared(row), mx_s = (unsigned)__cvta_generic_to_shared(MX),
                    my_s = (unsigned)__cvta_generic_to_shared(MY), mz_s = (unsigned)__cvta_generic_to_shared(MZ),
                    tab_s = (unsigned)__cvta_generic_to_shared(tab);
-    auto put = [&](unsigned pos, unsigned j, unsigned cw) {
+    auto put = [&](unsigned pos, unsigned j, unsigned code) {
       const unsigned slot = pos & 3u;
-      const unsigned cb = (unsigned)((unsigned long long)cw >> (slot * 16u)) & 0xe000u;   // slots 2, 3 shift the bits out
+      const unsigned cb = ((code >> (3u * slot)) & 7u) << 13;    // code < 32: slots 2, 3 get no bits
       *reinterpret_cast<uint16_t*>(li + (pos >> 2) * rowbytes + slot * 2u) = (uint16_t)(j | cb);
     };
     {
@@ -469,16 +472,17 @@ __device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
         while (m == 0u && ++w < W) { m = lds_u32(row_s + 4u * w); X = lds_u32(mx_s + 4u * w); Y = lds_u32(my_s + 4u * w); Z = lds_u32(mz_s + 4u * w); jb = 32u * w; }
         if (w >= W) break;
         const unsigned bit = (unsigned)__ffs(m) - 1u; m &= m - 1u;
-        const unsigned g = ((X >> bit) & 1u) | (((Y >> bit) & 1u) << 1) | (((Z >> bit) & 1u) << 2);
-        const unsigned ta = tab_s + g * gbytes;
-        const uint2 t = lds_u64(ta);
-        sts_u32(ta, t.x + 1u);
-        put(t.x, jb + bit, t.y);
+        const unsigned gx = (X >> bit) & 1u, gy = (Y >> bit) & 1u, gz = (Z >> bit) & 1u;
+        const unsigned ta = tab_s + (gx | (gy << 1) | (gz << 2)) * gbytes;
+        unsigned short pos;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pos) : "r"(ta));
+        asm volatile("st.shared.u16 [%0], %1;" :: "r"(ta), "h"((unsigned short)(pos + 1)) : "memory");
+        put(pos, jb + bit, (unsigned)(13 + (int)gx * cA + (int)gy * cB + (int)gz * cC));
       }
     }
 #pragma unroll
     for (int g = 0; g < 8; g++)                              // pad every group to a whole quad with the dummy atom
-      if (cg[g]) { const uint2 t = tab[g * nthr]; for (unsigned pos = t.x; pos & 3u; pos++) put(pos, (unsigned)N, t.y); }
+      if (cg[g]) { const unsigned code = (unsigned)(13 + (g & 1) * cA + ((g >> 1) & 1) * cB + ((g >> 2) & 1) * cC); for (unsigned pos = tab[g * nthr]; pos & 3u; pos++) put(pos, (unsigned)N, code); }
     cx.nnb[i] = (uint16_t)nq;
     cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
     tot += nT;
@@ -590,11 +594,7 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
     for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
     __syncthreads();
     for (int i = tid; i < N; i += nthr) {
-      const float4 p = cx.sf[i];
-      int a = min(nc - 1, (int)(p.x * nc)), b = min(nc - 1, (int)(p.y * nc)), e = min(nc - 1, (int)(p.z * nc));
-      int c = (a * nc + b) * nc + e;
-      cx.atom_cell[i] = (uint16_t)c;
-      atomicAdd(&cx.cell_cnt[c], 1);
+      atomicAdd(&cx.cell_cnt[cell_of(cx.sf[i], nc)], 1);
     }
     __syncthreads();
     if (tid < 32) {
@@ -611,7 +611,7 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
     for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
     __syncthreads();
     for (int i = tid; i < N; i += nthr) {
-      int c = cx.atom_cell[i];
+      const int c = cell_of(cx.sf[i], nc);
       int p = atomicAdd(&cx.cell_cnt[c], 1);
       cx.cell_atoms[cx.cell_start[c] + p] = (uint16_t)i;
     }
@@ -846,7 +846,13 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       const unsigned a0 = sp_s + 24u * (cur.x & 0x1fffu), a1 = sp_s + 24u * ((cur.x >> 16) & 0x1fffu),
                      a2 = sp_s + 24u * (cur.y & 0xffffu), a3 = sp_s + 24u * (cur.y >> 16);
       double p[12];
+#ifdef NM_PLAIN_GATHER
+      { const double *q0 = cx.sp + 3 * (cur.x & 0x1fffu), *q1 = cx.sp + 3 * ((cur.x >> 16) & 0x1fffu), *q2 = cx.sp + 3 * (cur.y & 0xffffu), *q3 = cx.sp + 3 * (cur.y >> 16);
+        p[0] = q0[0]; p[1] = q0[1]; p[2] = q0[2]; p[3] = q1[0]; p[4] = q1[1]; p[5] = q1[2];
+        p[6] = q2[0]; p[7] = q2[1]; p[8] = q2[2]; p[9] = q3[0]; p[10] = q3[1]; p[11] = q3[2]; (void)a0; (void)a1; (void)a2; (void)a3; }
+#else
       lds_f64x3(a0, p[0], p[1], p[2]); lds_f64x3(a1, p[3], p[4], p[5]); lds_f64x3(a2, p[6], p[7], p[8]); lds_f64x3(a3, p[9], p[10], p[11]);
+#endif
       lj_pair<EW, MIC>(p[0], p[1], p[2], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       lj_pair<EW, MIC>(p[3], p[4], p[5], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       lj_pair<EW, MIC>(p[6], p[7], p[8], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
