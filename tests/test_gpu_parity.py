@@ -472,6 +472,28 @@ def test_list_build_paths_across_box_to_list_ratio(nm, orc, skin):
         np.testing.assert_allclose(th[k, :9], th_o[:9], rtol=2e-9, atol=1e-9)
 
 
+def test_two_level_lists_in_a_small_dense_box(nm, orc):
+    """N = 864 (two-level lists) in a box below 2.5 outer radii: the outer search has no cell grid (all-atoms scan)"""
+    x, box = _configs(orc, 6, [1.25, 1.2], [0.03, 0.05], seed=17)        # L = 8.84, 8.96
+    box = np.array([orc.round6(b) for b in box])
+    with nm.Engine(natoms=864, n_rep=2, nt=2, mod=6, bulk_move=True, seed=23) as eng:
+        eng.set_labels([0.8, 1.6], [8.0 / 0.8, 8.0 / 1.6], [0.8, 1.6])
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[.03, .03], dv=[.03, .03], dt=[.004, .004])
+        pe, w, f, npairs = eng.eval()
+        for k in range(2):
+            pe_o, w_o, f_o, np_o = orc.lj_eval_list(x[k], box[k])
+            assert npairs[k] == np_o and abs(pe[k] - pe_o) <= 1e-10 * abs(pe_o) and abs(w[k] - w_o) <= 1e-10 * abs(w_o)
+            assert np.abs(f[k] - f_o).max() <= 1e-10 * np.abs(f_o).max()
+        eng.run_cycle(0)
+        th = eng.get_thermo()
+    params = orc.make_params(mod=6, bulk_move=1, seed=23)
+    for k, T in enumerate((0.8, 1.6)):
+        xo, vo = x[k].copy(), np.zeros(3 * 864)
+        th_o, _ = orc.cycle(params, [T, 8.0 / T, T, orc.round6(T)], k, 0, xo, vo, np.array([box[k], .03, .03, .004]), np.zeros(6))
+        np.testing.assert_array_equal(th[k, 9:], th_o[9:])
+        np.testing.assert_allclose(th[k, :9], th_o[:9], rtol=2e-9, atol=1e-9)
+
+
 # ------------------------------------------------------------------ size-independent properties at the BASELINE sizes
 @pytest.mark.parametrize("n_side", [5, 10])
 def test_eval_invariances_at_full_size(nm, orc, n_side):
