@@ -763,33 +763,36 @@ __device__ void check_list(const Dev& d, Ctx& cx) {
 // order like integers) and the masking a single select on the high word, so only arithmetic reaches the FP64 pipe:
 // 17 FP64-pipe instructions per pair for forces, +4 for energy and virial.
 // MIC: small boxes -- the minimum image is taken per pair (high-word test + FP64 subtract) instead.
-template <bool EW, bool MIC>
+template <bool EW, bool MIC, bool S32>
 __device__ __forceinline__ void lj_pair(double xj, double yj, double zj, double xs, double ys, double zs,
                                         int L_hi, int L_lo, int hL_hi, long long rc2_bits,
                                         double& fx, double& fy, double& fz, int& np, double& e, double& vir) {
   double dx = xs - xj, dy = ys - yj, dz = zs - zj;
   if (MIC) { dx = mic_fast(dx, L_hi, L_lo, hL_hi); dy = mic_fast(dy, L_hi, L_lo, hL_hi); dz = mic_fast(dz, L_hi, L_lo, hL_hi); }
   const double rsq = fma(dz, dz, fma(dy, dy, dx * dx));
-  // reciprocal: MUFU.RCP64H seed (2^-19.9, measured) + one cubic step (3 DFMA): relative error ~ 2^-59.
-  // Measured alternatives: FP32 MUFU.RCP seed + one Newton step (-DNM_RCP_F32SEED; the two F64<->F32 conversions
-  // cost two issue slots each: 3 % slower, 6e-14); cubic + quadratic step (-DNM_RCP_EXACT, < 1 ulp, 3 % slower)
-#if defined(NM_RCP_F32SEED)
-  float yf;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)rsq));
-  double y = (double)yf;
-  double t = fma(-rsq, y, 1.0);
-  const double r2inv = fma(y, t, y);
-#else
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
-  double t = fma(-rsq, y, 1.0);
-  t = fma(t, t, t);
+  // reciprocal, two variants chosen per kernel instantiation (S32 = the 1024-thread kernels):
+  //  * MUFU.RCP64H seed (2^-19.9, measured) + one cubic step (3 DFMA), relative error ~ 2^-59: best when two CTAs
+  //    share an SM and are usually in different phases (the conversions of the other variant cost two issue slots each);
+  //  * FP32 MUFU.RCP seed + one Newton step (2 DFMA + 2 conversions), 6e-14: best when one 1024-thread CTA keeps all
+  //    32 warps in the loop at once and the FP64 pipe itself is the contended unit (N = 4000: 131 vs 136 ms per step).
+  //  -DNM_RCP_EXACT adds a quadratic step to the first variant (< 1 ulp).
+  double r2inv;
+  if (S32) {
+    float yf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)rsq));
+    const double y = (double)yf, t = fma(-rsq, y, 1.0);
+    r2inv = fma(y, t, y);
+  } else {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
+    double t = fma(-rsq, y, 1.0);
+    t = fma(t, t, t);
 #if defined(NM_RCP_EXACT)
-  y = fma(y, t, y);
-  t = fma(-rsq, y, 1.0);
+    y = fma(y, t, y);
+    t = fma(-rsq, y, 1.0);
 #endif
-  const double r2inv = fma(y, t, y);
-#endif
+    r2inv = fma(y, t, y);
+  }
   const double r6inv = r2inv * r2inv * r2inv;
   double fpair = r6inv * fma(48.0, r6inv, -24.0) * r2inv;
   // outside the cutoff the high word is zeroed: the operand becomes a denormal (< 1e-308) whose products vanish.
@@ -814,7 +817,7 @@ __device__ __forceinline__ void lj_pair(double xj, double yj, double zj, double 
 // EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
 // half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
 // Ends with a barrier: shared positions may be rewritten afterwards.
-template <bool EW, bool KICK, bool MIC>
+template <bool EW, bool KICK, bool MIC, bool S32>
 __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
   const int N = cx.N, Npad = cx.Npad;
   const long long rc2_bits = __double_as_longlong(d.rc * d.rc);
@@ -853,10 +856,10 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
 #else
       lds_f64x3(a0, p[0], p[1], p[2]); lds_f64x3(a1, p[3], p[4], p[5]); lds_f64x3(a2, p[6], p[7], p[8]); lds_f64x3(a3, p[9], p[10], p[11]);
 #endif
-      lj_pair<EW, MIC>(p[0], p[1], p[2], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(p[3], p[4], p[5], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(p[6], p[7], p[8], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
-      lj_pair<EW, MIC>(p[9], p[10], p[11], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC, S32>(p[0], p[1], p[2], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC, S32>(p[3], p[4], p[5], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC, S32>(p[6], p[7], p[8], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+      lj_pair<EW, MIC, S32>(p[9], p[10], p[11], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       cur = nxt;
     }
     if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_atom0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
@@ -953,13 +956,13 @@ __device__ void eval_forces_f32(const Dev& d, Ctx& cx, double dtf, double (&out)
   }
 }
 
-template <bool EW, bool KICK>
+template <bool EW, bool KICK, bool S32>
 __device__ __forceinline__ void eval_forces(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
   if (d.f32) {
     if (cx.mic) eval_forces_f32<EW, KICK, true>(d, cx, dtf, out);
     else eval_forces_f32<EW, KICK, false>(d, cx, dtf, out);
-  } else if (cx.mic) eval_forces_t<EW, KICK, true>(d, cx, dtf, out);
-  else eval_forces_t<EW, KICK, false>(d, cx, dtf, out);
+  } else if (cx.mic) eval_forces_t<EW, KICK, true, S32>(d, cx, dtf, out);
+  else eval_forces_t<EW, KICK, false, S32>(d, cx, dtf, out);
 }
 
 // the acceptance rule shared by all moves (lammps_remcmc.py:487-500, 532-547, 578-593, 623-638)
@@ -1005,6 +1008,7 @@ __device__ void restore_xf(Ctx& cx, bool with_v) {
 }
 
 // ------------------------------------------------------------------ a-7 bulk_position_mc (lammps_remcmc.py:477-502)
+template <bool S32>
 __device__ void bulk_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double dxs, Energy& en, double* cnt) {
   save_xf(cx, false);
   const double dmax = d.text_rounding ? round6(dxs * d.lat) : dxs * d.lat;     // 'displace_atoms all random %f'
@@ -1018,7 +1022,7 @@ __device__ void bulk_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
     if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
   }
   sync_and_maybe_build(d, cx, flag);
-  double o[4]; eval_forces<true, false>(d, cx, 0.0, o);
+  double o[4]; eval_forces<true, false, S32>(d, cx, 0.0, o);
   bool acc = false;
   if (threadIdx.x == 0) {
     const double de = o[0] / et - en.pe / et;
@@ -1031,6 +1035,7 @@ __device__ void bulk_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
 }
 
 // ------------------------------------------------------------------ a-6 volume_mc (lammps_remcmc.py:552-595)
+template <bool S32>
 __device__ void volume_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double pf, double dvs, Energy& en, double* cnt) {
   save_xf(cx, false);
   const double box = cx.L;
@@ -1059,7 +1064,7 @@ __device__ void volume_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double
       if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
     }
     sync_and_maybe_build(d, cx, flag);
-    eval_forces<true, false>(d, cx, 0.0, o);
+    eval_forces<true, false, S32>(d, cx, 0.0, o);
   } else {
     cx.status |= ST_BOX;
   }
@@ -1204,6 +1209,7 @@ __device__ double velocity_create(const Dev& d, Ctx& cx, const Rng& r, double t_
 }
 
 // ------------------------------------------------------------------ a-3 / a-5 hamiltonian_mc (lammps_remcmc.py:598-640)
+template <bool S32>
 __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double t_vel, double dts, Energy& en, double* cnt) {
   const int N = cx.N, Npad = cx.Npad;
   const long long t_vel0 = clock64();
@@ -1226,8 +1232,8 @@ __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, d
       if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
     }
     sync_and_maybe_build(d, cx, flag);
-    if (st == d.nstps - 1) eval_forces<true, true>(d, cx, dtf, o);
-    else eval_forces<false, true>(d, cx, dtf, o);
+    if (st == d.nstps - 1) eval_forces<true, true, S32>(d, cx, dtf, o);
+    else eval_forces<false, true, S32>(d, cx, dtf, o);
   }
   bool acc = false;
   if (threadIdx.x == 0) {
@@ -1243,6 +1249,7 @@ __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, d
 // ------------------------------------------------------------------ a-8 iter_position_mc (lammps_remcmc.py:505-549)
 // The reference re-evaluates the whole system for each of the N sequential single-atom trials; here warp 0
 // walks the same sequential chain with the single-atom energy change summed over the atom's list column.
+template <bool S32>
 __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double dxs, Energy& en, double* cnt) {
   const int N = cx.N, Npad = cx.Npad, lane = threadIdx.x & 31;
   const double rc = d.rc, rc2 = rc * rc, rl = rc + d.skin, L = cx.L, hL = 0.5 * L, invL = 1.0 / L;
@@ -1345,7 +1352,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
   }
   // the state the last 'run 0' of the sweep leaves: a fresh full evaluation
   check_list(d, cx);
-  double o[4]; eval_forces<true, false>(d, cx, 0.0, o);
+  double o[4]; eval_forces<true, false, S32>(d, cx, 0.0, o);
   en.pe = o[0]; en.w = o[1];
 }
 
@@ -1354,6 +1361,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR, 1024 / NTHR)
 k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npairs_out) {
+  constexpr bool S32 = NTHR == 1024;
   extern __shared__ __align__(16) unsigned char smem[];
   Ctx cx; ctx_init(d, cx, blockIdx.x, smem);
   if (cx.L < 2.0 * d.rc * (1.0 + 1e-5)) { if (threadIdx.x == 0) d.status[cx.c] |= ST_BOX; return; }
@@ -1361,7 +1369,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
   update_thr(d, cx);
   __syncthreads();
   check_list(d, cx);
-  double o[4]; eval_forces<true, false>(d, cx, 0.0, o);
+  double o[4]; eval_forces<true, false, S32>(d, cx, 0.0, o);
   store_positions(cx);
   double t[1] = { 0 };
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
@@ -1390,6 +1398,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR, 1024 / NTHR)
 k_cycle(Dev d, long long cycle) {
+  constexpr bool S32 = NTHR == 1024;
   extern __shared__ __align__(16) unsigned char smem[];
   Ctx cx; ctx_init(d, cx, d.order[blockIdx.x], smem);
   const int c = cx.c, slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
@@ -1409,10 +1418,10 @@ k_cycle(Dev d, long long cycle) {
     const long long t_mv0 = clock64();
     const int kind = roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2);
     if (kind == 0) {
-      if (d.bulk) bulk_position_mc(d, cx, r, et, dxs, en, cnt);
-      else iter_position_mc(d, cx, r, et, dxs, en, cnt);
-    } else if (kind == 1) volume_mc(d, cx, r, et, pf, dvs, en, cnt);
-    else hamiltonian_mc(d, cx, r, et, t_vel, dts, en, cnt);
+      if (d.bulk) bulk_position_mc<S32>(d, cx, r, et, dxs, en, cnt);
+      else iter_position_mc<S32>(d, cx, r, et, dxs, en, cnt);
+    } else if (kind == 1) volume_mc<S32>(d, cx, r, et, pf, dvs, en, cnt);
+    else hamiltonian_mc<S32>(d, cx, r, et, t_vel, dts, en, cnt);
     if (threadIdx.x == 0) { cx.ct[NM_CT_SWEEPS]++; kclk[kind] += (unsigned long long)(clock64() - t_mv0); kcnt[kind]++; }
   }
   // lammps_extract
