@@ -494,6 +494,23 @@ def test_two_level_lists_in_a_small_dense_box(nm, orc):
         np.testing.assert_allclose(th[k, :9], th_o[:9], rtol=2e-9, atol=1e-9)
 
 
+def test_replica_counters_add_up_to_the_engine_counters(nm, orc):
+    """nm_get_replica_counters: the per-slot counters of the last cycle sum to the engine totals"""
+    x, box = _configs(orc, 4, [1.0, 0.9, 0.8, 0.7], [0.05] * 4, seed=3)
+    with nm.Engine(natoms=256, n_rep=4, nt=4, mod=12, bulk_move=True, seed=2) as eng:
+        T = np.array([0.6, 1.0, 1.4, 1.8])
+        eng.set_labels(T, 2.0 / T, T)
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=[.03] * 4, dv=[.03] * 4, dt=[.004] * 4)
+        eng.reset_counters()
+        eng.run_cycle(0)
+        tot, rep = eng.counters(), eng.replica_counters()
+    cols = {k: i for i, k in enumerate(nm.COUNTER_COLS)}
+    assert rep.shape == (4, nm.COUNTER_WIDTH)
+    for k in ("sweeps", "hmc_moves", "hmc_atom_steps", "vmc_moves", "pmc_moves", "force_evals", "list_builds", "pairs_full"):
+        assert int(rep[:, cols[k]].sum()) == tot[k], k
+    assert (rep[:, cols["sweeps"]] == 12).all()
+
+
 # ------------------------------------------------------------------ size-independent properties at the BASELINE sizes
 @pytest.mark.parametrize("n_side", [5, 10])
 def test_eval_invariances_at_full_size(nm, orc, n_side):
