@@ -45,14 +45,20 @@ def build(force=False, verbose=False):
     procs = []
     bdir = os.path.join(_HERE, "build")
     os.makedirs(bdir, exist_ok=True)
+    units = []
     for src in sources():
-        obj = os.path.join(bdir, os.path.basename(src) + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
-                                      "-c", src, "-o", obj]
+        if os.path.basename(src) == "nm_engine.cu":      # NM_TU: one unit per thread count + the host unit, built in parallel
+            units += [(src, ["-DNM_TU=%d" % t], ".tu%d" % t) for t in (512, 1024, 256, 0)]
+        else:
+            units.append((src, [], ""))
+    for src, defs, tag in units:
+        obj = os.path.join(bdir, os.path.basename(src) + tag + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + defs + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
+                                             "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
-        procs.append((src, subprocess.Popen(cmd)))
+        procs.append((src + tag, subprocess.Popen(cmd)))
         objs.append(obj)
     for src, p in procs:
         if p.wait() != 0:

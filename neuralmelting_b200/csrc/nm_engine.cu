@@ -106,6 +106,8 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
   return b;
 }
 
+namespace {   // device functions: internal linkage (this file is compiled as several translation units, see NM_TU)
+
 // block_sum on alternating scratch halves (see nm_device.cuh): one barrier per reduction
 template <int K>
 __device__ __forceinline__ void bsum(double (&v)[K], Ctx& cx) {
@@ -1356,6 +1358,9 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
   en.pe = o[0]; en.w = o[1];
 }
 
+}  // anonymous namespace
+
+
 // ------------------------------------------------------------------ kernels
 // 'run 0' on the resident configurations: wrap, (re)build list, evaluate; optionally export.
 template <int NTHR>
@@ -1457,6 +1462,35 @@ k_cycle(Dev d, long long cycle) {
   }
 }
 
+// ---- launchers, one set per thread count. build.py compiles this file four times (-DNM_TU=256 / 512 / 1024: the
+// kernels of that thread count only; -DNM_TU=0: the small kernels and the host C-ABI) so that the three heavy
+// instantiations build in parallel; without NM_TU everything lands in one translation unit.
+#define NM_LAUNCHERS(T)                                                                                              \
+  cudaError_t set_smem_##T(size_t sm) {                                                                              \
+    cudaError_t e = cudaFuncSetAttribute(k_cycle<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);          \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    return e;                                                                                                        \
+  }                                                                                                                  \
+  void launch_cycle_##T(const Dev& d, long long cycle, size_t sm, cudaStream_t st) { k_cycle<T><<<d.nrep, T, sm, st>>>(d, cycle); } \
+  void launch_eval_##T(const Dev& d, double* pe, double* w, double* f, long long* np_, size_t sm, cudaStream_t st) { \
+    k_eval<T><<<d.nrep, T, sm, st>>>(d, pe, w, f, np_);                                                              \
+  }
+#define NM_LAUNCHER_DECLS(T)                                                                                         \
+  cudaError_t set_smem_##T(size_t sm);                                                                               \
+  void launch_cycle_##T(const Dev& d, long long cycle, size_t sm, cudaStream_t st);                                  \
+  void launch_eval_##T(const Dev& d, double* pe, double* w, double* f, long long* np_, size_t sm, cudaStream_t st);
+NM_LAUNCHER_DECLS(256) NM_LAUNCHER_DECLS(512) NM_LAUNCHER_DECLS(1024)
+#if !defined(NM_TU) || NM_TU == 256
+NM_LAUNCHERS(256)
+#endif
+#if !defined(NM_TU) || NM_TU == 512
+NM_LAUNCHERS(512)
+#endif
+#if !defined(NM_TU) || NM_TU == 1024
+NM_LAUNCHERS(1024)
+#endif
+
+#if !defined(NM_TU) || NM_TU == 0
 // Cost-balanced CTA placement for the next cycle. Blocks b and b + nsm share an SM when two CTAs fit per SM and
 // nrep <= 2 nsm (the block scheduler fills SMs round-robin). With last cycle's per-configuration clocks sorted in
 // descending order, the nsm-(nrep-nsm) SMs that hold a single CTA get the most expensive configurations and every
@@ -1610,7 +1644,10 @@ __global__ void k_gather_state(Dev d, double* x_aos, double* v_aos, double* box,
   }
 }
 
+#endif  // small kernels
 }  // namespace nm
+
+#if !defined(NM_TU) || NM_TU == 0
 
 // =================================================================== host side / C-ABI
 using namespace nm;
@@ -1735,9 +1772,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   }
   cudaError_t e = cudaSuccess;
   const int sm = (int)h->smem;
-  if (h->threads == 256) { e = cudaFuncSetAttribute(k_cycle<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
-  else if (h->threads == 512) { e = cudaFuncSetAttribute(k_cycle<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
-  else { e = cudaFuncSetAttribute(k_cycle<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); }
+  e = h->threads == 256 ? set_smem_256(h->smem) : (h->threads == 512 ? set_smem_512(h->smem) : set_smem_1024(h->smem));
   if (e != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "cudaFuncSetAttribute(smem=%zu): %s", h->smem, cudaGetErrorString(e)); }
   *out = h;
   return NM_OK;
@@ -1779,9 +1814,9 @@ static int check_status(nm_engine* h) {
 }
 
 static int launch_eval(nm_engine* h, double* pe, double* w, double* f_aos, long long* np_) {
-  if (h->threads == 256) k_eval<256><<<h->d.nrep, 256, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
-  else if (h->threads == 512) k_eval<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
-  else k_eval<1024><<<h->d.nrep, 1024, h->smem, h->stream>>>(h->d, pe, w, f_aos, np_);
+  if (h->threads == 256) launch_eval_256(h->d, pe, w, f_aos, np_, h->smem, h->stream);
+  else if (h->threads == 512) launch_eval_512(h->d, pe, w, f_aos, np_, h->smem, h->stream);
+  else launch_eval_1024(h->d, pe, w, f_aos, np_, h->smem, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   return NM_OK;
@@ -1863,9 +1898,9 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
     h->launches++;
     CK(cudaGetLastError());
   }
-  if (h->threads == 256) k_cycle<256><<<h->d.nrep, 256, h->smem, h->stream>>>(h->d, (long long)cycle);
-  else if (h->threads == 512) k_cycle<512><<<h->d.nrep, 512, h->smem, h->stream>>>(h->d, (long long)cycle);
-  else k_cycle<1024><<<h->d.nrep, 1024, h->smem, h->stream>>>(h->d, (long long)cycle);
+  if (h->threads == 256) launch_cycle_256(h->d, (long long)cycle, h->smem, h->stream);
+  else if (h->threads == 512) launch_cycle_512(h->d, (long long)cycle, h->smem, h->stream);
+  else launch_cycle_1024(h->d, (long long)cycle, h->smem, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   h->have_thermo = true;
@@ -1977,3 +2012,4 @@ int nm_get_replica_counters(nm_engine* h, uint64_t* out) {
 }
 
 }  // extern "C"
+#endif  // host C-ABI
