@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--workload", type=str, default="c2", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--rdf-samples", type=int, default=1024, help="c5: samples per step (N = 4000, SBINS = 64)")
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
-    ap.add_argument("--equil", type=int, default=8, help="untimed equilibration cycles before the warm-up")
+    ap.add_argument("--equil", type=int, default=32, help="untimed equilibration cycles before the warm-up (the step sizes adapt for ~25 cycles: the cost of a cycle rises by 60 %% until the acceptances settle at 0.5)")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="pair arithmetic: 64 (headline) or the FP32 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
@@ -191,12 +191,25 @@ def run_b200(args):
     eng.reset_counters()
     comm.barrier(); torch.cuda.synchronize()
     w0 = time.perf_counter()
+    breakdown = os.environ.get("NM_BENCH_E2E_BREAKDOWN")          # development aid: synchronises after every call
+    tb = [0.0] * 4
+    kev_e2e = []
     for _ in range(e2e_steps):
+        c0 = time.perf_counter()
         eng.set_state(x=hx.numpy(), v=hv.numpy(), box=hbox, dx=hdx, dv=hdv, dt=hdt)      # H2D (+ the 'run 0' evaluation)
-        th = step(cyc); cyc += 1
-        st = eng.get_state()                                                          # D2H
-        hx.numpy()[:] = st["x"]; hv.numpy()[:] = st["v"]
+        if breakdown: eng.synchronize()
+        c1 = time.perf_counter()
+        th = step(cyc, kev_e2e if breakdown else None); cyc += 1
+        if breakdown: eng.synchronize()
+        c2 = time.perf_counter()
+        st = eng.get_state(x_out=hx.numpy(), v_out=hv.numpy())                       # D2H straight into the pinned host buffers
+        c3 = time.perf_counter()
         hbox, hdx, hdv, hdt = st["box"], st["dx"], st["dv"], st["dt"]
+        c4 = time.perf_counter()
+        for k, dtk in enumerate((c1 - c0, c2 - c1, c3 - c2, c4 - c3)): tb[k] += dtk
+    if breakdown and comm.rank == 0:
+        print("e2e breakdown (ms/step): set_state %.2f  step %.2f (cycle kernel %.2f)  get_state %.2f  host copies %.2f" % (
+            1e3 * tb[0] / e2e_steps, 1e3 * tb[1] / e2e_steps, sum(a.elapsed_time(b) for a, b in kev_e2e) / e2e_steps, 1e3 * tb[2] / e2e_steps, 1e3 * tb[3] / e2e_steps), file=sys.stderr)
     torch.cuda.synchronize(); comm.barrier()
     e2e_s = time.perf_counter() - w0
     ct_e2e = eng.counters()

@@ -104,8 +104,8 @@ typedef struct nm_config {
   double   lat_scale;       /* LAT[EL][1] (1.122): displacement scale factor               */
   double   mass;            /* MASS[EL]                                                    */
   double   rc;              /* lj/cut cutoff (2.5); epsilon = sigma = 1                    */
-  double   skin;            /* inner Verlet-list skin; <= 0 selects the default (0.3)      */
-  double   skin_outer;      /* extra radius of the outer list; <= 0 selects the default (1.0) */
+  double   skin;            /* inner Verlet-list skin; <= 0 selects the default (0.4 for natoms <= 768, else 0.3) */
+  double   skin_outer;      /* extra radius of the outer list; <= 0 selects the default (1.3) */
   uint64_t seed;            /* counter-based RNG seed (reference: SEED = 256)              */
   void*    stream;          /* cudaStream_t to launch on; NULL = engine-owned stream       */
 } nm_config;

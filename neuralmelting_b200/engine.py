@@ -164,9 +164,15 @@ class Engine:
         box, dx, dv, dt = (_f64(a, (self.n_rep,)) for a in (box, dx, dv, dt))
         _check(self._L.nm_set_state(self._h, _ptr(x), _ptr(v), _ptr(box), _ptr(dx), _ptr(dv), _ptr(dt)))
 
-    def get_state(self, want_x=True, want_v=True):
-        x = np.empty((self.n_rep, 3 * self.natoms)) if want_x else None
-        v = np.empty((self.n_rep, 3 * self.natoms)) if want_v else None
+    def get_state(self, want_x=True, want_v=True, x_out=None, v_out=None):
+        """state of every local slot; x_out / v_out: caller-owned C-contiguous float64 (n_rep, 3 natoms) arrays to fill
+        in place (pinned memory makes the device-to-host copy run at PCIe speed and saves a host copy)"""
+        n3 = (self.n_rep, 3 * self.natoms)
+        for a in (x_out, v_out):
+            if a is not None and not (a.dtype == np.float64 and a.shape == n3 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("get_state: output arrays must be C-contiguous float64 of shape %s" % (n3,))
+        x = x_out if x_out is not None else (np.empty(n3) if want_x else None)
+        v = v_out if v_out is not None else (np.empty(n3) if want_v else None)
         box, dx, dv, dt = (np.empty(self.n_rep) for _ in range(4))
         _check(self._L.nm_get_state(self._h, _ptr(x), _ptr(v), _ptr(box), _ptr(dx), _ptr(dv), _ptr(dt)))
         return dict(x=x, v=v, box=box, dx=dx, dv=dv, dt=dt)
