@@ -29,8 +29,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one nm::k_cycle launch from the committed `ncu --set full` capture
-# (profiles/r1b_cycle_c2_ncu_full.txt); per workload, None where no capture exists
-NCU_TRAFFIC_BYTES = {"c2": 93.4912e6 + 1127.401e6}
+# (profiles/r1c_cycle_c2_ncu_full.txt); per workload, None where no capture exists
+NCU_TRAFFIC_BYTES = {"c2": 256.89856e6 + 2662.470e6}
 
 WORKLOADS = {
     # name: (supercell, pressure rows per GPU, temperatures, bulk_move, ppos, pvol, mod, description)
@@ -241,7 +241,7 @@ def run_b200(args):
                     "steps": e2e_steps, "note": "set_state (pinned host x, v, box, step sizes) -> cycle -> get_thermo + get_state, every step"},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "fp64_fma" if args.precision == 64 else "fp32_fma", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if comm.world == 1 else None, "traffic_unit": "bytes/launch (ncu capture, profiles/r1b_cycle_c2_ncu_full.txt)",
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if comm.world == 1 else None, "traffic_unit": "bytes/launch (ncu capture, profiles/r1c_cycle_c2_ncu_full.txt)",
                          "kernel": "nm::k_cycle", "kernel_ms_per_step": kernel_ms / args.steps,
                          "peak_source": "live DFMA microbenchmark (nm_measure_fma_peak); MEASURED_PEAKS.json carries no FP64 figure",
                          "flops": "24/in-cutoff pair (force), 30 (force+energy+virial), 13/neighbour of a single-atom dE, 18/atom-step",
