@@ -62,6 +62,29 @@ def test_lj_eval_fcc_anchor(nm, orc):
         assert np.abs(f).max() < 1e-11
 
 
+def test_lammps_melt_example_step0_pins_the_cuda_path(nm, orc):
+    """third-party pin (LAMMPS examples/melt, step-0 thermo line shipped with LAMMPS: E_pair -6.7733681, TotEng -2.2744931,
+    Press -3.7033504 at T = 3): nm_eval and the cycle kernel's lammps_extract (temp, pe, ke, virial = thermo_press with
+    dof = 3N - 3) reproduce every printed digit"""
+    from test_oracle_lj import MELT_EPAIR, MELT_PRESS, MELT_RHO, MELT_T, MELT_TOTENG, melt_thermo
+    n, box = 4000, 10 * (4 / MELT_RHO) ** (1 / 3)
+    x = orc.fcc_positions(10, box).reshape(1, -1)
+    rng = np.random.default_rng(87287)
+    v = rng.normal(0, 1, (n, 3))
+    v -= v.mean(0)
+    v *= np.sqrt(MELT_T * (3 * n - 3) / (v ** 2).sum())             # 'velocity all create 3.0': T = sum m v^2 / (3N-3) exactly
+    with nm.Engine(natoms=n, n_rep=1, nt=1, mod=0, text_rounding=False) as eng:
+        eng.set_labels([MELT_T], [1.0], [MELT_T], [MELT_T])
+        eng.set_state(x=x, v=v.reshape(1, -1), box=[box], dx=[.03], dv=[.03], dt=[.004])
+        pe, w, f, npairs = eng.eval()
+        eng.run_cycle(0)                                            # mod = 0: lammps_extract only
+        th = eng.get_thermo()[0]
+    e_pair, toteng, press = melt_thermo(n, pe[0], w[0], box, MELT_T)
+    assert abs(e_pair - MELT_EPAIR) < 5e-8 and abs(toteng - MELT_TOTENG) < 5e-8 and abs(press - MELT_PRESS) < 5e-8
+    assert abs(th[0] - MELT_T) < 1e-12 and abs(th[1] / n - MELT_EPAIR) < 5e-8
+    assert abs((th[1] + th[2]) / n - MELT_TOTENG) < 5e-8 and abs(th[3] - MELT_PRESS) < 5e-8
+
+
 def test_box_too_small_is_an_error(nm, orc):
     x = orc.fcc_positions(3, 4.9).reshape(1, -1)
     with nm.Engine(natoms=108, n_rep=1, nt=1) as eng:
@@ -71,7 +94,8 @@ def test_box_too_small_is_an_error(nm, orc):
 
 
 # ------------------------------------------------------------------ a-2..a-9 cycle, move by move
-def _run_both(nm, orc, n_side, bulk, mod, ncycles, rho, temps, press, seed=256, dx0=0.03125):
+def _run_both(nm, orc, n_side, bulk, mod, ncycles, rho, temps, press, seed=256, dx0=0.03125, dv0=0.03125, dt0=0.00390625,
+              ppos=0.125, pvol=0.125, **engine_kw):
     n = 4 * n_side ** 3
     nrep = len(temps)
     x, box = _configs(orc, n_side, rho, [0.05] * nrep, seed=11)
@@ -79,9 +103,9 @@ def _run_both(nm, orc, n_side, bulk, mod, ncycles, rho, temps, press, seed=256, 
     T = np.array(temps, dtype=np.float32).astype(np.float64)
     P = np.array(press, dtype=np.float32).astype(np.float64)
     labels = np.stack([T, P / T, T, [orc.round6(t) for t in T]], 1)
-    params = orc.make_params(mod=mod, bulk_move=int(bulk), seed=seed)
+    params = orc.make_params(mod=mod, bulk_move=int(bulk), seed=seed, ppos=ppos, pvol=pvol)
     xo, vo = x.copy(), np.zeros_like(x)
-    scal = np.stack([box, np.full(nrep, dx0), np.full(nrep, 0.03125), np.full(nrep, 0.00390625)], 1).copy()
+    scal = np.stack([box, np.full(nrep, dx0), np.full(nrep, dv0), np.full(nrep, dt0)], 1).copy()
     counts = np.zeros((nrep, 6))
     th_o = []
     for cyc in range(ncycles):
@@ -93,10 +117,10 @@ def _run_both(nm, orc, n_side, bulk, mod, ncycles, rho, temps, press, seed=256, 
             counts[k] = 0
         th_o.append(np.array(rows))
     th_g = []
-    with nm.Engine(natoms=n, n_rep=nrep, nt=nrep, mod=mod, bulk_move=bulk, seed=seed) as eng:
+    with nm.Engine(natoms=n, n_rep=nrep, nt=nrep, mod=mod, bulk_move=bulk, seed=seed, ppos=ppos, pvol=pvol, **engine_kw) as eng:
         eng.set_labels(labels[:, 0], labels[:, 1], labels[:, 2], labels[:, 3])
-        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(nrep, dx0), dv=np.full(nrep, 0.03125),
-                      dt=np.full(nrep, 0.00390625))
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(nrep, dx0), dv=np.full(nrep, dv0),
+                      dt=np.full(nrep, dt0))
         for cyc in range(ncycles):
             eng.run_cycle(cyc)
             th_g.append(eng.get_thermo())
@@ -125,6 +149,58 @@ def test_cycle_matches_oracle_move_by_move(nm, orc, bulk):
     assert np.abs(st["v"] - vo).max() < 1e-8
     assert ct["sweeps"] == 4 * 24 * 3
     assert ct["hmc_atom_steps"] == 256 * 8 * ct["hmc_moves"]
+
+
+def _assert_cycle_parity(th_o, th_g, xo, vo, scal, st):
+    """counters and float32 ratios exact, thermo 2e-9, step sizes, final positions (mod box) and velocities 1e-8"""
+    np.testing.assert_array_equal(th_g[..., 9:15], th_o[..., 9:15])
+    np.testing.assert_array_equal(th_g[..., 15:18], th_o[..., 15:18])
+    np.testing.assert_allclose(th_g[..., :9], th_o[..., :9], rtol=2e-9, atol=1e-9)
+    np.testing.assert_allclose(st["box"], scal[:, 0], rtol=0, atol=0)
+    np.testing.assert_allclose(st["dx"], scal[:, 1], rtol=1e-15)
+    np.testing.assert_allclose(st["dv"], scal[:, 2], rtol=1e-15)
+    np.testing.assert_allclose(st["dt"], scal[:, 3], rtol=1e-15)
+    d = st["x"] - xo
+    d -= st["box"][:, None] * np.rint(d / st["box"][:, None])
+    assert np.abs(d).max() < 1e-8
+    assert np.abs(st["v"] - vo).max() < 1e-8
+
+
+@pytest.mark.parametrize("bulk,dx0", [(True, 0.03125), (True, 0.004), (False, 0.03125)])
+def test_cycle_parity_n500_the_benchmarked_kernel(nm, orc, bulk, dx0):
+    """N = 500 is BASELINE configs[1] (k_cycle<512>: two CTAs per SM, bin-mask list builds at production box sizes).
+    A cold solid, two states near melting and a hot fluid, three cycles with adaptation in between so that the lists
+    are rebuilt under motion; dx0 = 0.004 makes bulk displacements acceptable (the default 0.03125 never is)."""
+    th_o, th_g, (xo, vo, scal), st, ct = _run_both(nm, orc, 5, bulk, mod=24, ncycles=3, rho=[1.1, 1.0, 0.85, 0.6],
+                                                   temps=[0.4, 0.9, 1.6, 2.5], press=[1, 3, 5, 8], dx0=dx0)
+    _assert_cycle_parity(th_o, th_g, xo, vo, scal, st)
+    tot = th_o[..., 9:15].sum((0, 1))
+    assert tot[4] > tot[5] > 0 and tot[2] > tot[3] > 0            # HMC and VMC: accepts and rejects both present
+    if bulk and dx0 < 0.01:
+        assert tot[0] > tot[1] > 0                                # bulk PMC accepts and rejects
+    if not bulk:
+        assert tot[0] >= 500 and tot[0] > tot[1] > 0              # single-atom trials
+    assert ct["sweeps"] == 4 * 24 * 3 and ct["hmc_atom_steps"] == 500 * 8 * ct["hmc_moves"]
+    assert ct["list_builds"] > 4 * 3                              # lists were rebuilt under motion
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+def test_cycle_parity_n4000_the_north_star_kernel(nm, orc, bulk):
+    """N = 4000 (BASELINE configs[2], [3]; k_cycle<1024>): the multi-atom-per-thread velocity_create, the cell-grid outer
+    build and the inner regeneration under motion (skin_outer = 0.25 forces outer rebuilds inside the run), the FP32-seeded
+    reciprocal inside trajectories (6e-14 per pair: far inside the 2e-9 thermo tolerance), VMC accept + reject, HMC
+    accept + reject, and with bulk=False the software-pipelined single-atom walker."""
+    kw = dict(mod=12, ppos=0.25, pvol=0.25) if bulk else dict(mod=6, ppos=0.34, pvol=0.33)
+    th_o, th_g, (xo, vo, scal), st, ct = _run_both(nm, orc, 10, bulk, ncycles=2, rho=[1.1, 0.95, 0.6], temps=[0.4, 1.2, 2.5],
+                                                   press=[4, 3, 2], dv0=0.01, dt0=0.006, skin_outer=0.25, **kw)
+    _assert_cycle_parity(th_o, th_g, xo, vo, scal, st)
+    tot = th_o[..., 9:15].sum((0, 1))
+    assert tot[4] > tot[5] > 0 and tot[2] > tot[3] > 0 and tot[0] > tot[1] > 0
+    if not bulk:
+        assert tot[0] >= 4000
+    assert ct["hmc_atom_steps"] == 4000 * 8 * ct["hmc_moves"]
+    assert ct["outer_builds"] > 3                                 # more than the initial build of each replica
+    assert ct["list_builds"] > ct["outer_builds"]                 # inner regenerations from a surviving outer list
 
 
 def test_cycle_hmc_only_matches_oracle(nm, orc):

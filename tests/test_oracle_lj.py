@@ -88,3 +88,34 @@ def test_cycle_invariants(orc):
     assert abs(th[0] - 2 * th[2] / dof) < 1e-12
     # pe of the trace's last row equals the reported pe
     assert tr[-1, 0] == th[1]
+
+
+# LAMMPS examples/melt (in.melt: `lattice fcc 0.8442`, `region box block 0 10 0 10 0 10`, `velocity all create 3.0 87287`,
+# `pair_style lj/cut 2.5`, `pair_coeff 1 1 1.0 1.0 2.5`), step-0 thermo line of the logs LAMMPS ships with the example
+# (log.*.melt.g++.*): "Step Temp E_pair E_mol TotEng Press" = 0 3 -6.7733681 0 -2.2744931 -3.7033504 (per-atom energies,
+# lj units). It pins energy, virial and the 3N-3 dof convention of thermo_temp / thermo_press to LAMMPS's own output.
+MELT_RHO, MELT_T = 0.8442, 3.0
+MELT_EPAIR, MELT_TOTENG, MELT_PRESS = -6.7733681, -2.2744931, -3.7033504
+
+
+def melt_thermo(n, pe, w, box, temp):
+    """thermo_pe / N, (pe + ke) / N and thermo_press with ke = dof/2 k_B T, dof = 3N - 3 (what `velocity create` leaves)"""
+    dof = 3 * n - 3
+    ke = 0.5 * dof * temp
+    return pe / n, (pe + ke) / n, (dof * temp + w) / (3.0 * box ** 3)
+
+
+def test_lammps_melt_example_step0_pins_the_oracle(orc):
+    """third-party pin: the oracle reproduces every printed digit of LAMMPS's published step-0 line for this potential"""
+    a = (4 / MELT_RHO) ** (1 / 3)
+    n, box = 4000, 10 * a
+    x = orc.fcc_positions(10, box)
+    for ev in (orc.lj_eval_list, orc.lj_eval_n2):
+        pe, w, f, npairs = ev(x, box)
+        e_pair, toteng, press = melt_thermo(n, pe, w, box, MELT_T)
+        assert abs(e_pair - MELT_EPAIR) < 5e-8
+        assert abs(toteng - MELT_TOTENG) < 5e-8
+        assert abs(press - MELT_PRESS) < 5e-8
+        assert np.abs(f).max() < 1e-11
+    e, wn, nn = orc.fcc_shell_sum(a)
+    assert abs(e - MELT_EPAIR) < 5e-8 and npairs == n * nn // 2
