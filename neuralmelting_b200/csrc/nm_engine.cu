@@ -39,16 +39,19 @@ struct Dev {
   double ppos, pvol, lat, mass, rc, skin, oskin;
   uint32_t seed_lo, seed_hi;
   // per configuration
-  double *x, *v, *f, *xs, *vs, *fs, *x0;   // [nrep][3][Npad]
-  ushort4* list;                           // [nrep][maxq][Npad]  neighbour quads, grouped by periodic image
-  uint8_t* qcode;                          // [nrep][maxq][Npad]  image code (0..26) of each quad
+  double *x, *v, *f, *xs, *vs, *fs;        // [nrep][3][Npad]
+  double* x0;                              // [nrep][2][3][Npad]  fractional coordinates at the build of list buffer 0 / 1
+  ushort4* list;                           // [nrep][2][maxq + 1][Npad]  neighbour quads, grouped by periodic image; TWO buffers per
+                                           // configuration: a build inside a move goes to the other buffer, so a rejected move
+                                           // switches back to the list that was valid for the saved positions
+  int* lcur;                               // [nrep] which buffer holds the current list
   uint32_t* ltmp;                          // [nrep][maxnbo][Npad] outer-build scratch: j | code << 16 in discovery order
   ushort4* olist;                          // [nrep][maxqo][Npad] OUTER list (radius rc+skin+oskin), same grouped format
   uint8_t* ocode;                          // [nrep][maxqo][Npad]
   uint16_t* onq;                           // [nrep][Npad]
   double* x0o;                             // [nrep][3][Npad] fractional coordinates at the last outer build
   double* L0o;                             // [nrep] box at the last outer build
-  uint16_t* nnb;                           // [nrep][Npad]        number of quads of atom i
+  uint16_t* nnb;                           // [nrep][2][Npad]     number of quads of atom i (per list buffer)
   int* micmode;                            // [nrep] 1: box < 2(rc+skin) at build, images resolved per pair
   double *box, *pe, *w, *ke, *L0;          // [nrep]
   double *step;                            // [nrep][3]  dx dv dt
@@ -70,7 +73,6 @@ struct Dev {
 struct Ctx {
   int N, Npad, c;
   double L, L0, thr2;           // box, list build box, squared displacement budget (build-box units)
-  double Lsave;                 // box the saved copy (gxs) refers to
   double* sp;                   // shared positions, AoS: atom j at sp[3j..3j+2] (one address register per gather)
   float4* sf;                   // shared float32 fractional positions (list build prefilter only)
   uint32_t* hbits;              // shared (small mode): N x N hit bit matrix, row i = atoms within the list radius of i
@@ -82,13 +84,19 @@ struct Ctx {
   unsigned long long* s_pairs;  // shared: in-cutoff ordered pairs of force-only evaluations
   // global views of this configuration
   double *gx, *gv, *gf, *gxs, *gvs, *gfs, *gx0;
-  ushort4* list; uint8_t* qcode; uint32_t* ltmp; uint16_t* nnb;
+  ushort4* list; uint32_t* ltmp; uint16_t* nnb;
   ushort4* olist; uint8_t* ocode; uint16_t* onq; double* gx0o;
   double L0o, thro2;            // outer list: build box and squared displacement budget
   double* sht;                  // shared: 27 image shift vectors (k*L) for the current box
   int mic;                      // minimum image per pair (small boxes) instead of stored image codes
-  unsigned long long ct[NM_COUNTER_WIDTH];   // meaningful on thread 0 only
+  unsigned long long* ct;       // shared: NM_COUNTER_WIDTH counters, touched by thread 0 only
   double list_pairs;
+  // double-buffered lists: lbuf = buffer of the current list; inside a move (in_move) the first build switches to
+  // the other buffer and leaves the list of the saved positions (sv_*) intact for a revert
+  int lbuf, in_move, sv_lbuf, sv_mic, outer_in_move;
+  double sv_L0, sv_list_pairs;
+  ushort4* list_base; uint16_t* nnb_base; double* gx0_base;
+  size_t list_stride;           // quads per list buffer
   int status;
   int redflip;                  // which half of `red` the next block_sum uses
 };
@@ -99,7 +107,7 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
   size_t b = sizeof(double) * (3 * (size_t)Npad + RED_DOUBLES + BC_DOUBLES + SHT_DOUBLES);
   b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8 + 2);   // +2: keeps the float4 block 16-byte aligned
   b += sizeof(float4) * (size_t)Npad;
-  b += sizeof(unsigned long long) * 2;
+  b += sizeof(unsigned long long) * (2 + NM_COUNTER_WIDTH);
   b += sizeof(uint16_t) * (size_t)Npad;
   if (small) b += sizeof(uint32_t) * hbits_words(N) + sizeof(uint16_t) * 8 * (size_t)nthr;   // two 512-thread CTAs stay under the 164 KB carve-out
   else b += sizeof(uint16_t) * 8 * (size_t)nthr;          // outer build: per-thread group counters / cursors
@@ -116,6 +124,13 @@ __device__ __forceinline__ void bsum(double (&v)[K], Ctx& cx) {
   block_sum<K>(v, cx.red + cx.redflip * RED_HALF);
 }
 
+// point the list views at buffer cx.lbuf
+__device__ __forceinline__ void select_list(Ctx& cx) {
+  cx.list = cx.list_base + (size_t)cx.lbuf * cx.list_stride;
+  cx.nnb = cx.nnb_base + (size_t)cx.lbuf * cx.Npad;
+  cx.gx0 = cx.gx0_base + (size_t)cx.lbuf * 3 * cx.Npad;
+}
+
 __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned char* smem) {
   cx.redflip = 0;
   cx.N = d.N; cx.Npad = d.Npad; cx.c = c;
@@ -125,6 +140,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.bc = p; p += BC_DOUBLES;
   cx.sht = p; p += SHT_DOUBLES;
   cx.s_pairs = reinterpret_cast<unsigned long long*>(p); p += 2;
+  cx.ct = reinterpret_cast<unsigned long long*>(p); p += NM_COUNTER_WIDTH;
   int* q = reinterpret_cast<int*>(p);
   cx.cell_cnt = q; q += NCMAX * NCMAX * NCMAX + 1;
   cx.cell_start = q; q += NCMAX * NCMAX * NCMAX + 1;
@@ -137,21 +153,23 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.gcur = reinterpret_cast<uint16_t*>(cx.hbits);                                           // LARGE mode only (no hit matrix there)
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
-  cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off; cx.gx0 = d.x0 + off;
-  cx.list = d.list + (size_t)c * d.maxq * d.Npad;
-  cx.qcode = d.qcode + (size_t)c * d.maxq * d.Npad;
+  cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off;
+  cx.list_stride = (size_t)(d.maxq + 1) * d.Npad;
+  cx.list_base = d.list + (size_t)c * 2 * cx.list_stride;
+  cx.nnb_base = d.nnb + (size_t)c * 2 * d.Npad;
+  cx.gx0_base = d.x0 + 2 * off;
+  cx.lbuf = d.lcur[c]; cx.in_move = 0; cx.sv_lbuf = cx.lbuf; cx.outer_in_move = 0;
+  select_list(cx);
   cx.ltmp = d.ltmp + (size_t)c * ((d.maxnbo + 3) & ~3) * d.Npad;     // [entry][atom]
   cx.olist = d.olist + (size_t)c * d.maxqo * d.Npad;
   cx.ocode = d.ocode + (size_t)c * d.maxqo * d.Npad;
   cx.onq = d.onq + (size_t)c * d.Npad;
   cx.gx0o = d.x0o + off;
   cx.L0o = d.L0o[c];
-  cx.nnb = d.nnb + (size_t)c * d.Npad;
   cx.mic = d.micmode[c];
-  cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.Lsave = cx.L; cx.list_pairs = d.list_pairs[c];
+  cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.list_pairs = d.list_pairs[c];
   cx.status = 0;
-  for (int k = 0; k < NM_COUNTER_WIDTH; k++) cx.ct[k] = 0;
-  if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; }
+  if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; for (int k = 0; k < NM_COUNTER_WIDTH; k++) cx.ct[k] = 0; }
 }
 
 // displacement budgets for box L (s = L/L0): inner list complete while s*(rl - 2u) >= rc; the outer list can
@@ -496,8 +514,10 @@ __device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
 }
 
 
-// re-wrap every atom into [0,L) (shifting the revert copy by the same lattice vector) and refresh the float32
-// fractional copies; entries N..Npad-1 are parked far away so that padded indices never test positive
+// re-wrap every atom into [0,L) and refresh the float32 fractional copies; entries N..Npad-1 are parked far away so
+// that padded indices never test positive. The revert copy of a move in flight is NOT shifted: a build inside a move
+// goes to the other list buffer, and a rejected move returns to the saved positions together with the list (and its
+// periodic images) that was valid for them.
 __device__ void wrap_and_refresh(Ctx& cx, bool wrap) {
   const int N = cx.N, Npad = cx.Npad;
   const double L = cx.L, invL = 1.0 / L;
@@ -507,7 +527,7 @@ __device__ void wrap_and_refresh(Ctx& cx, bool wrap) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
           const double x = cx.sp[3 * i + a], xw = wrap1(x - floor(x * invL) * L, L);
-          if (xw != x) { cx.sp[3 * i + a] = xw; cx.gxs[a * Npad + i] += (xw - x) * (cx.Lsave * invL); }
+          if (xw != x) cx.sp[3 * i + a] = xw;
         }
       }
       cx.sf[i] = make_float4((float)(cx.sp[3 * i] * invL), (float)(cx.sp[3 * i + 1] * invL), (float)(cx.sp[3 * i + 2] * invL), 0.f);
@@ -723,6 +743,7 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
 // (re)build: make sure the outer list can still supply every pair within rl, then regenerate the inner list
 __device__ void build_list(const Dev& d, Ctx& cx) {
   const long long t_build0 = clock64();
+  if (cx.in_move && cx.lbuf == cx.sv_lbuf) { cx.lbuf ^= 1; select_list(cx); }   // keep the list of the saved positions
   if (d.small) {
     build_small(d, cx);
     if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; const unsigned long long dt = (unsigned long long)(clock64() - t_build0); cx.ct[NM_CT_CLK_BUILD] += dt; cx.ct[NM_CT_CLK_INNER] += dt; }
@@ -734,7 +755,7 @@ __device__ void build_list(const Dev& d, Ctx& cx) {
     for (int i = threadIdx.x; i < cx.N; i += blockDim.x)
       flag |= disp2o(cx, i, cx.sp[3 * i], cx.sp[3 * i + 1], cx.sp[3 * i + 2], invL) > cx.thro2;
   }
-  if (__syncthreads_or(flag)) { const long long t0 = clock64(); build_outer(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t0); }
+  if (__syncthreads_or(flag)) { const long long t0 = clock64(); cx.outer_in_move = cx.in_move; build_outer(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t0); }
   { const long long t0 = clock64(); build_inner(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_INNER] += (unsigned long long)(clock64() - t0); }
   if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; cx.ct[NM_CT_CLK_BUILD] += (unsigned long long)(clock64() - t_build0); }
 }
@@ -827,7 +848,9 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
   double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
   const long long t_eval0 = clock64();
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
+#ifdef NM_DEBUG_CLOCKS
     const long long t_atom0 = clock64();
+#endif
     const double xi = cx.sp[3 * i], yi = cx.sp[3 * i + 1], zi = cx.sp[3 * i + 2];
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const int nq = cx.nnb[i];
@@ -864,7 +887,9 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       lj_pair<EW, MIC, S32>(p[9], p[10], p[11], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       cur = nxt;
     }
+#ifdef NM_DEBUG_CLOCKS   // per-atom loop clocks of thread 0 (tools/probe.py); compiled out of the product build
     if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_atom0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
+#endif
     cx.gf[i] = fx; cx.gf[Npad + i] = fy; cx.gf[2 * Npad + i] = fz;
     if (KICK) {
       const double vx = fma(dtf, fx, cx.gv[i]), vy = fma(dtf, fy, cx.gv[Npad + i]), vz = fma(dtf, fz, cx.gv[2 * Npad + i]);
@@ -985,7 +1010,7 @@ __device__ __forceinline__ bool broadcast_flag(Ctx& cx, bool v) {
 struct Energy { double pe, w; };
 
 __device__ void save_xf(Ctx& cx, bool with_v) {
-  cx.Lsave = cx.L;
+  cx.in_move = 1; cx.sv_lbuf = cx.lbuf; cx.sv_L0 = cx.L0; cx.sv_mic = cx.mic; cx.sv_list_pairs = cx.list_pairs; cx.outer_in_move = 0;
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -996,7 +1021,16 @@ __device__ void save_xf(Ctx& cx, bool with_v) {
     }
   }
 }
-__device__ void restore_xf(Ctx& cx, bool with_v) {
+// rejected move: back to the saved positions (cx.L already restored by the caller) and to the list that was current when
+// they were saved; an outer list rebuilt inside the move refers to re-wrapped positions and is dropped
+__device__ void restore_xf(const Dev& d, Ctx& cx, bool with_v) {
+  if (cx.lbuf != cx.sv_lbuf) {
+    cx.lbuf = cx.sv_lbuf; select_list(cx);
+    cx.L0 = cx.sv_L0; cx.mic = cx.sv_mic; cx.list_pairs = cx.sv_list_pairs;
+    if (cx.outer_in_move) cx.L0o = -1.0;
+  }
+  cx.in_move = 0;
+  update_thr(d, cx);
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -1033,7 +1067,7 @@ __device__ void bulk_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
     cx.ct[NM_CT_PMC_MOVES]++; cx.ct[NM_CT_PMC_TRIALS]++;
   }
   acc = broadcast_flag(cx, acc);
-  if (acc) { en.pe = o[0]; en.w = o[1]; } else restore_xf(cx, false);
+  if (acc) { en.pe = o[0]; en.w = o[1]; cx.in_move = 0; } else restore_xf(d, cx, false);
 }
 
 // ------------------------------------------------------------------ a-6 volume_mc (lammps_remcmc.py:552-595)
@@ -1079,8 +1113,8 @@ __device__ void volume_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double
     cx.ct[NM_CT_VMC_MOVES]++;
   }
   acc = broadcast_flag(cx, acc);
-  if (acc) { en.pe = o[0]; en.w = o[1]; }
-  else { cx.L = box; update_thr(d, cx); if (box_ok) restore_xf(cx, false); }
+  if (acc) { en.pe = o[0]; en.w = o[1]; cx.in_move = 0; }
+  else { cx.L = box; if (box_ok) restore_xf(d, cx, false); else { cx.in_move = 0; update_thr(d, cx); } }
 }
 
 // ------------------------------------------------------------------ a-4 velocity create + zero linear + zero angular
@@ -1245,7 +1279,7 @@ __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, d
     cx.ct[NM_CT_HMC_MOVES]++; cx.ct[NM_CT_HMC_ATOM_STEPS] += (unsigned long long)N * d.nstps;
   }
   acc = broadcast_flag(cx, acc);
-  if (acc) { en.pe = o[0]; en.w = o[1]; } else restore_xf(cx, true);
+  if (acc) { en.pe = o[0]; en.w = o[1]; cx.in_move = 0; } else restore_xf(d, cx, true);
 }
 
 // ------------------------------------------------------------------ a-8 iter_position_mc (lammps_remcmc.py:505-549)
@@ -1390,7 +1424,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
     }
   }
   if (threadIdx.x == 0) {
-    d.pe[cx.c] = o[0]; d.w[cx.c] = o[1]; d.ke[cx.c] = 0.5 * d.mass * t[0]; d.L0[cx.c] = cx.L0; d.L0o[cx.c] = cx.L0o; d.micmode[cx.c] = cx.mic; d.list_pairs[cx.c] = cx.list_pairs;
+    d.pe[cx.c] = o[0]; d.w[cx.c] = o[1]; d.ke[cx.c] = 0.5 * d.mass * t[0]; d.L0[cx.c] = cx.L0; d.L0o[cx.c] = cx.L0o; d.micmode[cx.c] = cx.mic; d.list_pairs[cx.c] = cx.list_pairs; d.lcur[cx.c] = cx.lbuf;
     if (pe_out) pe_out[slot] = o[0];
     if (w_out) w_out[slot] = o[1];
     if (npairs_out) npairs_out[slot] = (long long)o[2];
@@ -1448,7 +1482,7 @@ k_cycle(Dev d, long long cycle) {
       const float a = (float)cnt[2 * k + 1] / (float)cnt[2 * k];        // float32 ratio, nan_to_num (0/0 -> 0)
       th[NM_TH_AP + k] = isnan(a) ? 0.0 : (double)a;
     }
-    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.L0o[c] = cx.L0o; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs;
+    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.L0o[c] = cx.L0o; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs; d.lcur[c] = cx.lbuf;
     if (cx.status) d.status[c] |= cx.status;
     cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
     const unsigned long long dt_cycle = (unsigned long long)(clock64() - t_cycle0);
@@ -1749,9 +1783,9 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   d.nsm = h->nsm; d.per_sm = (h->smem * 2 <= 220 * 1024 && h->threads <= 512) ? 2 : 1;
   if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
   const size_t per = (size_t)nrep * 3 * d.Npad;
-  DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, per);
-  DA(d.list, ((size_t)nrep * d.maxq + 2) * d.Npad); DA(d.qcode, (size_t)nrep * d.maxq * d.Npad);
-  DA(d.ltmp, (size_t)nrep * ((d.maxnbo + 3) & ~3) * d.Npad); DA(d.nnb, (size_t)nrep * d.Npad); DA(d.micmode, nrep);
+  DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, 2 * per);
+  DA(d.list, ((size_t)nrep * 2 * (d.maxq + 1) + 2) * d.Npad); DA(d.lcur, nrep);       // one spare row per buffer: the loop prefetches one quad ahead
+  DA(d.ltmp, (size_t)nrep * ((d.maxnbo + 3) & ~3) * d.Npad); DA(d.nnb, (size_t)nrep * 2 * d.Npad); DA(d.micmode, nrep);
   DA(d.olist, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.ocode, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.onq, (size_t)nrep * d.Npad);
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);

@@ -184,23 +184,26 @@ def test_cycle_parity_n500_the_benchmarked_kernel(nm, orc, bulk, dx0):
     assert ct["list_builds"] > 4 * 3                              # lists were rebuilt under motion
 
 
-@pytest.mark.parametrize("bulk", [True, False])
-def test_cycle_parity_n4000_the_north_star_kernel(nm, orc, bulk):
+@pytest.mark.parametrize("bulk,skin_outer", [(True, 0.25), (True, 0.0), (False, 0.25)])
+def test_cycle_parity_n4000_the_north_star_kernel(nm, orc, bulk, skin_outer):
     """N = 4000 (BASELINE configs[2], [3]; k_cycle<1024>): the multi-atom-per-thread velocity_create, the cell-grid outer
-    build and the inner regeneration under motion (skin_outer = 0.25 forces outer rebuilds inside the run), the FP32-seeded
-    reciprocal inside trajectories (6e-14 per pair: far inside the 2e-9 thermo tolerance), VMC accept + reject, HMC
-    accept + reject, and with bulk=False the software-pipelined single-atom walker."""
+    build and the inner regeneration under motion (skin_outer = 0.25 forces outer rebuilds inside the run, the default
+    1.3 regenerates inner lists from a surviving outer list), the FP32-seeded reciprocal inside trajectories (6e-14 per
+    pair: far inside the 2e-9 thermo tolerance), VMC accept + reject, HMC accept + reject, and with bulk=False the
+    software-pipelined single-atom walker."""
     kw = dict(mod=12, ppos=0.25, pvol=0.25) if bulk else dict(mod=6, ppos=0.34, pvol=0.33)
     th_o, th_g, (xo, vo, scal), st, ct = _run_both(nm, orc, 10, bulk, ncycles=2, rho=[1.1, 0.95, 0.6], temps=[0.4, 1.2, 2.5],
-                                                   press=[4, 3, 2], dv0=0.01, dt0=0.006, skin_outer=0.25, **kw)
+                                                   press=[4, 3, 2], dv0=0.01, dt0=0.006, skin_outer=skin_outer, **kw)
     _assert_cycle_parity(th_o, th_g, xo, vo, scal, st)
     tot = th_o[..., 9:15].sum((0, 1))
     assert tot[4] > tot[5] > 0 and tot[2] > tot[3] > 0 and tot[0] > tot[1] > 0
     if not bulk:
         assert tot[0] >= 4000
     assert ct["hmc_atom_steps"] == 4000 * 8 * ct["hmc_moves"]
-    assert ct["outer_builds"] > 3                                 # more than the initial build of each replica
-    assert ct["list_builds"] > ct["outer_builds"]                 # inner regenerations from a surviving outer list
+    if skin_outer > 0:
+        assert ct["outer_builds"] > 3                             # outer rebuilds under motion, beyond the initial one per replica
+    else:
+        assert ct["list_builds"] > ct["outer_builds"] >= 3        # inner regenerations from a surviving outer list
 
 
 def test_cycle_hmc_only_matches_oracle(nm, orc):
