@@ -22,11 +22,15 @@ namespace nm {
 
 constexpr int NCMAX = 10;                // cell grid is at most 10^3 (N = 4000 must stay below the 196 KB shared-memory carve-out: L1 keeps 60 KB)
 constexpr int RED_HALF = 32 * 9;           // one block_sum scratch area (K <= 9)
-static_assert(3 * 16 * 25 <= 2 * (NCMAX * NCMAX * NCMAX + 1), "bin masks of the SMALL builds live in the idle cell arrays");
 constexpr int RED_DOUBLES = 2 * RED_HALF;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
-constexpr int NSMALL = 768;              // largest N handled by the all-pairs hit-matrix build (72 KB of bits)
+constexpr int NSMALL = 768;              // largest N handled by the all-pairs hit-matrix build (SMALL mode: one atom per thread)
+// SMALL mode resolves periodic images with GHOST atoms: the shared position array is extended by the shifted copies of
+// the atoms within the list radius of a box face (up to 7 per atom), and the list stores the index of the copy to use.
+// Capacity: expected (1 + 2 r/L)^3 - 1 <= 5.45 copies per atom while r/L < 0.43; beyond the capacity (or in boxes
+// below 2 r_list) the build falls back to the per-pair minimum image.
+__host__ __device__ inline int ghost_cap(int N) { return ((int)(5.6 * N) + 33) & ~1; }
 constexpr int ST_BOX = 1, ST_NEIGH = 2;  // status bits
 
 // ------------------------------------------------------------------ device-side engine description
@@ -45,6 +49,9 @@ struct Dev {
                                            // configuration: a build inside a move goes to the other buffer, so a rejected move
                                            // switches back to the list that was valid for the saved positions
   int* lcur;                               // [nrep] which buffer holds the current list
+  uint32_t* hbT;                           // SMALL mode: [nrep][Npad/32][Npad] OUTER list = symmetric hit bit matrix (radius rc+skin+oskin),
+                                           // word-major ("transposed": word w of row i at [w][i], coalesced over atoms)
+  uint32_t* ginfo;                         // SMALL mode: [nrep][2][Npad] ghost table of each list buffer: base << 8 | lower-half bits << 3 | near-face bits
   uint32_t* ltmp;                          // [nrep][maxnbo][Npad] outer-build scratch: j | code << 16 in discovery order
   ushort4* olist;                          // [nrep][maxqo][Npad] OUTER list (radius rc+skin+oskin), same grouped format
   uint8_t* ocode;                          // [nrep][maxqo][Npad]
@@ -75,12 +82,15 @@ struct Ctx {
   double L, L0, thr2;           // box, list build box, squared displacement budget (build-box units)
   double* sp;                   // shared positions, AoS: atom j at sp[3j..3j+2] (one address register per gather)
   float4* sf;                   // shared float32 fractional positions (list build prefilter only)
-  uint32_t* hbits;              // shared (small mode): N x N hit bit matrix, row i = atoms within the list radius of i
+  uint32_t* hbT;                // global (SMALL mode): N x N hit bit matrix (outer list), word-major
+  uint32_t* ginfo;              // shared (SMALL mode): ghost table of the current list, one word per atom
+  uint32_t* ginfo_g;            // global copies of the ghost table, one per list buffer
+  uint8_t* gtbl;                // shared (SMALL mode): rank of image subset g among the subsets of a near-face mask, [8][8]
+  int* iscan;                   // shared: block-scan scratch (34 ints)
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
   uint16_t* cell_atoms;
   uint16_t* gcur;               // shared (LARGE mode): [8][nthr] per-thread group counters / cursors of the outer build
-  uint16_t* gtab;               // shared (SMALL mode): [8][nthr] per-thread cursors of the 8 image groups
   unsigned long long* s_pairs;  // shared: in-cutoff ordered pairs of force-only evaluations
   // global views of this configuration
   double *gx, *gv, *gf, *gxs, *gvs, *gfs, *gx0;
@@ -88,7 +98,8 @@ struct Ctx {
   ushort4* olist; uint8_t* ocode; uint16_t* onq; double* gx0o;
   double L0o, thro2;            // outer list: build box and squared displacement budget
   double* sht;                  // shared: 27 image shift vectors (k*L) for the current box
-  int mic;                      // minimum image per pair (small boxes) instead of stored image codes
+  int mic;                      // minimum image per pair (small boxes) instead of stored image codes / ghost copies
+  int ghost;                    // SMALL mode, current list uses ghost indices: position updates maintain the copies
   unsigned long long* ct;       // shared: NM_COUNTER_WIDTH counters, touched by thread 0 only
   double list_pairs;
   // double-buffered lists: lbuf = buffer of the current list; inside a move (in_move) the first build switches to
@@ -101,16 +112,20 @@ struct Ctx {
   int redflip;                  // which half of `red` the next block_sum uses
 };
 
-// rows are padded to an odd number of words: consecutive atoms (lanes) then hit different banks
-__host__ __device__ inline size_t hbits_words(int N) { const size_t w = (N + 31) / 32; return w * 32 * (w | 1); }
+// shared-memory carve (ctx_init): doubles first (positions [+ ghost copies], reduction / broadcast scratch, image shifts,
+// counters), then the float4 fractional copies (16-byte aligned: every count above is even), then the mode's integers
 __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nthr) {
   size_t b = sizeof(double) * (3 * (size_t)Npad + RED_DOUBLES + BC_DOUBLES + SHT_DOUBLES);
-  b += sizeof(int) * (2 * (NCMAX * NCMAX * NCMAX + 1) + 8 + 2);   // +2: keeps the float4 block 16-byte aligned
-  b += sizeof(float4) * (size_t)Npad;
+  if (small) b += sizeof(double) * 3 * (size_t)ghost_cap(N);
   b += sizeof(unsigned long long) * (2 + NM_COUNTER_WIDTH);
-  b += sizeof(uint16_t) * (size_t)Npad;
-  if (small) b += sizeof(uint32_t) * hbits_words(N) + sizeof(uint16_t) * 8 * (size_t)nthr;   // two 512-thread CTAs stay under the 164 KB carve-out
-  else b += sizeof(uint16_t) * 8 * (size_t)nthr;          // outer build: per-thread group counters / cursors
+  b += sizeof(float4) * (size_t)Npad;
+  b += sizeof(int) * (8 + 2 + 34);                              // ibc, iscan
+  if (small) b += sizeof(uint32_t) * (size_t)Npad + 64;         // ghost table, subset-rank table
+  else {
+    b += sizeof(int) * 2 * (NCMAX * NCMAX * NCMAX + 1);         // cell counts / starts
+    b += sizeof(uint16_t) * (size_t)Npad;                       // cell members
+    b += sizeof(uint16_t) * 8 * (size_t)nthr;                   // outer build: per-thread group counters / cursors
+  }
   return b;
 }
 
@@ -136,21 +151,36 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.N = d.N; cx.Npad = d.Npad; cx.c = c;
   double* p = reinterpret_cast<double*>(smem);
   cx.sp = p; p += 3 * d.Npad;
+  if (d.small) p += 3 * ghost_cap(d.N);      // ghost copies: entries Npad .. Npad + ghost_cap - 1 of sp
   cx.red = p; p += RED_DOUBLES;
   cx.bc = p; p += BC_DOUBLES;
   cx.sht = p; p += SHT_DOUBLES;
   cx.s_pairs = reinterpret_cast<unsigned long long*>(p); p += 2;
   cx.ct = reinterpret_cast<unsigned long long*>(p); p += NM_COUNTER_WIDTH;
-  int* q = reinterpret_cast<int*>(p);
-  cx.cell_cnt = q; q += NCMAX * NCMAX * NCMAX + 1;
-  cx.cell_start = q; q += NCMAX * NCMAX * NCMAX + 1;
+  cx.sf = reinterpret_cast<float4*>(p);
+  int* q = reinterpret_cast<int*>(cx.sf + d.Npad);
   cx.ibc = q; q += 8 + 2;
-  cx.sf = reinterpret_cast<float4*>(q); q += 4 * d.Npad;
-  uint16_t* h = reinterpret_cast<uint16_t*>(q);
-  cx.cell_atoms = h;
-  cx.hbits = reinterpret_cast<uint32_t*>(h + d.Npad);
-  cx.gtab = reinterpret_cast<uint16_t*>(cx.hbits + hbits_words(d.N));                        // SMALL mode only
-  cx.gcur = reinterpret_cast<uint16_t*>(cx.hbits);                                           // LARGE mode only (no hit matrix there)
+  cx.iscan = q; q += 34;
+  if (d.small) {
+    cx.ginfo = reinterpret_cast<uint32_t*>(q); q += d.Npad;
+    cx.gtbl = reinterpret_cast<uint8_t*>(q);
+    cx.cell_cnt = cx.cell_start = nullptr; cx.cell_atoms = nullptr; cx.gcur = nullptr;
+    // rank of the image subset g (bit a: shifted along axis a) among the non-empty subsets of the near-face mask nb
+    if (threadIdx.x < 64) {
+      const int nb = threadIdx.x >> 3, g = threadIdx.x & 7;
+      int r = 0, sh = 0;
+      for (int a = 0; a < 3; a++) if ((nb >> a) & 1) { r |= ((g >> a) & 1) << sh; sh++; }
+      cx.gtbl[threadIdx.x] = (uint8_t)r;
+    }
+  } else {
+    cx.cell_cnt = q; q += NCMAX * NCMAX * NCMAX + 1;
+    cx.cell_start = q; q += NCMAX * NCMAX * NCMAX + 1;
+    cx.cell_atoms = reinterpret_cast<uint16_t*>(q);
+    cx.gcur = cx.cell_atoms + d.Npad;
+    cx.ginfo = nullptr; cx.gtbl = nullptr;
+  }
+  cx.hbT = d.small ? d.hbT + (size_t)c * (d.Npad / 32) * d.Npad : nullptr;
+  cx.ginfo_g = d.small ? d.ginfo + (size_t)c * 2 * d.Npad : nullptr;
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
   cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off;
@@ -202,10 +232,34 @@ __device__ __forceinline__ double disp2o(const Ctx& cx, int i, double x, double 
 // positions global -> shared, plus the far-away dummy atom that pads the list. Positions are CONTINUOUS between
 // list builds (an atom may sit slightly outside [0,L)): the list stores the periodic image of every pair, so
 // atoms are re-wrapped only when the list is rebuilt.
+// GHOST copies of atom i (SMALL mode, cx.ghost): for every non-empty subset g of the faces the atom is near (nb), the
+// copy shifted by +L along the axes of g where the atom sits in the lower half of the box, -L in the upper half; the
+// copies of one atom are consecutive, ordered by g (= by gtbl rank). Called by whoever rewrites sp[3i..3i+2].
+__device__ __forceinline__ void write_ghosts(Ctx& cx, int i, double x, double y, double z) {
+  const uint32_t gi = cx.ginfo[i];
+  const unsigned nb = gi & 7u;
+  if (nb == 0u) return;
+  const double L = cx.L;
+  const double xs = x + ((gi & 8u) ? L : -L), ys = y + ((gi & 16u) ? L : -L), zs = z + ((gi & 32u) ? L : -L);
+  double* q = cx.sp + 3 * (size_t)(cx.Npad + (gi >> 8));
+#pragma unroll
+  for (unsigned g = 1; g < 8; g++)
+    if ((g & ~nb) == 0u) { q[0] = (g & 1u) ? xs : x; q[1] = (g & 2u) ? ys : y; q[2] = (g & 4u) ? zs : z; q += 3; }
+}
+// the one way to move atom i
+__device__ __forceinline__ void store_pos(Ctx& cx, int i, double x, double y, double z) {
+  cx.sp[3 * i] = x; cx.sp[3 * i + 1] = y; cx.sp[3 * i + 2] = z;
+  if (cx.ghost) write_ghosts(cx, i, x, y, z);
+}
+// ghost table of list buffer cx.lbuf -> shared (the owner's entry: read by the owner only until the next build)
+__device__ __forceinline__ void load_ginfo(Ctx& cx) {
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) cx.ginfo[i] = cx.ginfo_g[(size_t)cx.lbuf * cx.Npad + i];
+}
+
 __device__ void load_positions(const Dev& d, Ctx& cx) {
-  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
-    cx.sp[3 * i] = cx.gx[i]; cx.sp[3 * i + 1] = cx.gx[cx.Npad + i]; cx.sp[3 * i + 2] = cx.gx[2 * cx.Npad + i];
-  }
+  cx.ghost = d.small && !cx.mic && cx.L0 > 0.0;
+  if (cx.ghost) load_ginfo(cx);
+  for (int i = threadIdx.x; i < cx.N; i += blockDim.x) store_pos(cx, i, cx.gx[i], cx.gx[cx.Npad + i], cx.gx[2 * cx.Npad + i]);
   for (int i = cx.N + threadIdx.x; i < cx.Npad; i += blockDim.x) { cx.sp[3 * i] = 1e9; cx.sp[3 * i + 1] = 1e9; cx.sp[3 * i + 2] = 1e9; }
 }
 __device__ void store_positions(Ctx& cx) {
@@ -327,192 +381,12 @@ __device__ int outer_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
   return over;
 }
 
-// SMALL mode extraction: the owner walks its bit row twice. Pass 1 counts the hits per image group (8 packed 16-bit
-// counters), pass 2 stores every index straight into its final slot of the [quad][atom] layout using packed per-group
-// cursors -- two passes whatever the number of groups, no scratch memory. Image codes ride in the top 3 bits of the
-// first two indices of each quad; groups are padded to whole quads with the dummy atom N.
-__device__ int extract_rows_small(const Dev& d, Ctx& cx) {
-  const int N = cx.N, Npad = cx.Npad, W = (N + 31) / 32, WS = W | 1;
-  const double invL = 1.0 / cx.L;
-  const bool grouped = !cx.mic;
-  uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
-  int over = 0; double tot = 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const float4 pi = cx.sf[i];
-    const uint32_t* row = cx.hbits + (size_t)i * WS;
-    // image group of a listed neighbour: along an axis the fractional difference of a pair within the list radius
-    // is either below r_list/L < 1/2 in magnitude (same image) or above 1 - r_list/L > 1/2 (adjacent image)
-    auto group_of = [&](int j) -> int {
-      if (!grouped) return 0;
-      const float4 pj = cx.sf[j];
-      return (fabsf(pi.x - pj.x) > 0.5f) | ((fabsf(pi.y - pj.y) > 0.5f) << 1) | ((fabsf(pi.z - pj.z) > 0.5f) << 2);
-    };
-    unsigned long long c_lo = 0ull, c_hi = 0ull;
-    int cnt = 0;
-    // flattened walk over the set bits: every lane advances through ITS hits, so a warp iterates max(hits) times
-    // instead of sum over words of max(popcount)
-    {
-      int w = 0; uint32_t m = row[0];
-      for (;;) {
-        while (m == 0u && ++w < W) m = row[w];
-        if (w >= W) break;
-        const int j = w * 32 + __ffs(m) - 1; m &= m - 1;
-        const int g = group_of(j);
-        if (g < 4) c_lo += 1ull << (16 * g); else c_hi += 1ull << (16 * (g - 4));
-        cnt++;
-      }
-    }
-    // exclusive prefix of the quad-padded group sizes -> start slot (in entries) of every group
-    unsigned long long s_lo = 0ull, s_hi = 0ull;
-    int run = 0;
-#pragma unroll
-    for (int g = 0; g < 8; g++) {
-      const int ng = (int)(((g < 4 ? c_lo >> (16 * g) : c_hi >> (16 * (g - 4)))) & 0xffffull);
-      if (g < 4) s_lo |= (unsigned long long)run << (16 * g); else s_hi |= (unsigned long long)run << (16 * (g - 4));
-      run += (ng + 3) & ~3;
-    }
-    const int nq = run >> 2;
-    if (nq > d.maxq) { over = 1; cx.nnb[i] = 0; continue; }
-    const int sx = pi.x < 0.5f ? -1 : 1, sy = pi.y < 0.5f ? -1 : 1, sz = pi.z < 0.5f ? -1 : 1;
-    unsigned long long codes = 0ull;                       // the 8 group codes, 5 bits each
-#pragma unroll
-    for (int g = 0; g < 8; g++) codes |= (unsigned long long)(13 + 9 * (g & 1) * sx + 3 * ((g >> 1) & 1) * sy + ((g >> 2) & 1) * sz) << (5 * g);
-    auto put = [&](int pos, int j, int g) {
-      const int code = (int)(codes >> (5 * g)) & 31;
-      const int slot = pos & 3;
-      const int v = j | (slot == 0 ? (code & 7) << 13 : (slot == 1 ? (code >> 3) << 13 : 0));
-      l16[((size_t)(pos >> 2) * Npad + i) * 4 + slot] = (uint16_t)v;
-    };
-    unsigned long long f_lo = s_lo, f_hi = s_hi;           // running cursors
-    {
-      int w = 0; uint32_t m = row[0];
-      for (;;) {
-        while (m == 0u && ++w < W) m = row[w];
-        if (w >= W) break;
-        const int j = w * 32 + __ffs(m) - 1; m &= m - 1;
-        const int g = group_of(j);
-        const int pos = (int)(((g < 4 ? f_lo >> (16 * g) : f_hi >> (16 * (g - 4)))) & 0xffffull);
-        if (g < 4) f_lo += 1ull << (16 * g); else f_hi += 1ull << (16 * (g - 4));
-        put(pos, j, g);
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < 8; g++) {                           // pad every group to a whole quad with the dummy atom
-      int pos = (int)(((g < 4 ? f_lo >> (16 * g) : f_hi >> (16 * (g - 4)))) & 0xffffull);
-      const int ng = (int)(((g < 4 ? c_lo >> (16 * g) : c_hi >> (16 * (g - 4)))) & 0xffffull);
-      if (ng) for (; pos & 3; pos++) put(pos, N, g);
-    }
-    cx.nnb[i] = (uint16_t)nq;
-    cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
-    tot += cnt;
-  }
-  double r[1] = { tot };
-  bsum<1>(r, cx);
-  cx.list_pairs = 0.5 * r[0];
-  return over;
-}
-
 __device__ __forceinline__ uint32_t lds_u32(unsigned a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds_u64(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void lds_f64x3(unsigned a, double& x, double& y, double& z) {
   asm volatile("ld.shared.f64 %0, [%3];\n\tld.shared.f64 %1, [%3+8];\n\tld.shared.f64 %2, [%3+16];" : "=d"(x), "=d"(y), "=d"(z) : "r"(a));
 }
 __device__ __forceinline__ void sts_u32(unsigned a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-
-// SMALL mode extraction, box >= ~2.3 r_list (the usual case). The image group of a listed pair follows from 16
-// position bins per axis: a listed pair is separated by < 7/16 (same image) or > 9/16 (adjacent image) of the box
-// along every axis, so "wrapped along a" <=> the bins differ by >= 8. bin_masks() leaves, per axis and bin b, the
-// bit row of the atoms whose bin differs from b by >= 8; the owner of row i then
-//   pass 1: gets its 8 group sizes from 8 popcounts per 32-bit word of its hit row (inclusion-exclusion), and
-//   pass 2: walks the set bits once (flattened walk: a warp iterates max(hits) times), reads the group of a hit
-//           from three mask bits and stores the index straight into its final slot of the [quad][atom] layout
-//           through a per-thread cursor table in shared memory.
-__device__ void bin_masks(Ctx& cx) {
-  const int N = cx.N, W = (N + 31) / 32, WS = W | 1;
-  uint32_t* M = reinterpret_cast<uint32_t*>(cx.cell_cnt);          // [3][16][WS] (the cell arrays are idle in SMALL mode)
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int w = wid; w < W; w += nw) {
-    const int j = w * 32 + lane;
-    const float4 p = cx.sf[j < cx.Npad ? j : cx.Npad - 1];
-    const int b[3] = { min(15, (int)(p.x * 16.f)), min(15, (int)(p.y * 16.f)), min(15, (int)(p.z * 16.f)) };
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const uint32_t m = __ballot_sync(0xffffffffu, k < 8 ? b[a] >= k + 8 : b[a] <= k - 8);
-        if (lane == 0) M[(a * 16 + k) * WS + w] = m;
-      }
-  }
-}
-
-__device__ int extract_rows_bins(const Dev& d, Ctx& cx) {
-  const int N = cx.N, Npad = cx.Npad, W = (N + 31) / 32, WS = W | 1, nthr = blockDim.x;
-  const double invL = 1.0 / cx.L;
-  const uint32_t* M = reinterpret_cast<const uint32_t*>(cx.cell_cnt);
-  uint16_t* l16 = reinterpret_cast<uint16_t*>(cx.list);
-  uint16_t* tab = cx.gtab + threadIdx.x;                   // cursor of group g: tab[g * nthr]
-  int over = 0; double tot = 0.0;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const float4 pi = cx.sf[i];
-    const uint32_t* row = cx.hbits + (size_t)i * WS;
-    const int bx = min(15, (int)(pi.x * 16.f)), by = min(15, (int)(pi.y * 16.f)), bz = min(15, (int)(pi.z * 16.f));
-    const uint32_t *MX = M + bx * WS, *MY = M + (16 + by) * WS, *MZ = M + (32 + bz) * WS;
-    int nT = 0, nX = 0, nY = 0, nZ = 0, nXY = 0, nXZ = 0, nYZ = 0, nXYZ = 0;
-    for (int w = 0; w < W; w++) {
-      const uint32_t m = row[w], X = MX[w] & m, Y = MY[w], Z = MZ[w];
-      nT += __popc(m); nX += __popc(X); nY += __popc(m & Y); nZ += __popc(m & Z);
-      nXY += __popc(X & Y); nXZ += __popc(X & Z); nYZ += __popc(m & Y & Z); nXYZ += __popc(X & Y & Z);
-    }
-    const int cg[8] = { nT - nX - nY - nZ + nXY + nXZ + nYZ - nXYZ, nX - nXY - nXZ + nXYZ, nY - nXY - nYZ + nXYZ, nXY - nXYZ,
-                        nZ - nXZ - nYZ + nXYZ, nXZ - nXYZ, nYZ - nXYZ, nXYZ };
-    // image code of group g: -1 along an axis for atoms in the lower half of the box, +1 in the upper half
-    const int sx = bx < 8 ? -1 : 1, sy = by < 8 ? -1 : 1, sz = bz < 8 ? -1 : 1;
-    const int cA = 9 * sx, cB = 3 * sy, cC = sz;           // code of group g = 13 + (g&1) cA + (g>>1&1) cB + (g>>2&1) cC
-    int run = 0;
-#pragma unroll
-    for (int g = 0; g < 8; g++) { tab[g * nthr] = (uint16_t)run; run += (cg[g] + 3) & ~3; }
-    const int nq = run >> 2;
-    if (nq > d.maxq) { over = 1; cx.nnb[i] = 0; continue; }
-    // pass 2 runs on explicit 32-bit shared addresses (no generic-pointer arithmetic inside the loop)
-    char* li = reinterpret_cast<char*>(l16 + (size_t)i * 4);
-    asm volatile("" : "+l"(li));                            // keep the row base in registers (ptxas rematerialises it per store)
-    const unsigned rowbytes = (unsigned)Npad * 8u, gbytes = (unsigned)nthr * 2u;
-    const unsigned row_s = (unsigned)__cvta_generic_to_shared(row), mx_s = (unsigned)__cvta_generic_to_shared(MX),
-                   my_s = (unsigned)__cvta_generic_to_shared(MY), mz_s = (unsigned)__cvta_generic_to_shared(MZ),
-                   tab_s = (unsigned)__cvta_generic_to_shared(tab);
-    auto put = [&](unsigned pos, unsigned j, unsigned code) {
-      const unsigned slot = pos & 3u;
-      const unsigned cb = ((code >> (3u * slot)) & 7u) << 13;    // code < 32: slots 2, 3 get no bits
-      *reinterpret_cast<uint16_t*>(li + (pos >> 2) * rowbytes + slot * 2u) = (uint16_t)(j | cb);
-    };
-    {
-      int w = 0; unsigned jb = 0u;
-      uint32_t m = lds_u32(row_s), X = lds_u32(mx_s), Y = lds_u32(my_s), Z = lds_u32(mz_s);
-      for (;;) {
-        while (m == 0u && ++w < W) { m = lds_u32(row_s + 4u * w); X = lds_u32(mx_s + 4u * w); Y = lds_u32(my_s + 4u * w); Z = lds_u32(mz_s + 4u * w); jb = 32u * w; }
-        if (w >= W) break;
-        const unsigned bit = (unsigned)__ffs(m) - 1u; m &= m - 1u;
-        const unsigned gx = (X >> bit) & 1u, gy = (Y >> bit) & 1u, gz = (Z >> bit) & 1u;
-        const unsigned ta = tab_s + (gx | (gy << 1) | (gz << 2)) * gbytes;
-        unsigned short pos;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pos) : "r"(ta));
-        asm volatile("st.shared.u16 [%0], %1;" :: "r"(ta), "h"((unsigned short)(pos + 1)) : "memory");
-        put(pos, jb + bit, (unsigned)(13 + (int)gx * cA + (int)gy * cB + (int)gz * cC));
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < 8; g++)                              // pad every group to a whole quad with the dummy atom
-      if (cg[g]) { const unsigned code = (unsigned)(13 + (g & 1) * cA + ((g >> 1) & 1) * cB + ((g >> 2) & 1) * cC); for (unsigned pos = tab[g * nthr]; pos & 3u; pos++) put(pos, (unsigned)N, code); }
-    cx.nnb[i] = (uint16_t)nq;
-    cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
-    tot += nT;
-  }
-  double r[1] = { tot };
-  bsum<1>(r, cx);
-  cx.list_pairs = 0.5 * r[0];
-  return over;
-}
-
 
 // re-wrap every atom into [0,L) and refresh the float32 fractional copies; entries N..Npad-1 are parked far away so
 // that padded indices never test positive. The revert copy of a move in flight is NOT shifted: a build inside a move
@@ -531,27 +405,25 @@ __device__ void wrap_and_refresh(Ctx& cx, bool wrap) {
         }
       }
       cx.sf[i] = make_float4((float)(cx.sp[3 * i] * invL), (float)(cx.sp[3 * i + 1] * invL), (float)(cx.sp[3 * i + 2] * invL), 0.f);
-    } else cx.sf[i] = make_float4(1e6f, 1e6f, 1e6f, 0.f);
+    } else cx.sf[i] = make_float4(1e6f, 1e6f, 1e6f, 1e30f);     // .w: added to r^2 by the FP32-mode loop (the minimum image would fold the dummy back)
   }
 }
 
-// SMALL mode (N <= NSMALL): every unordered pair is tested ONCE, 32 x 32 tile by tile, on the FP32 pipe; the warp
-// ballot of each column gives the transposed bits, so both rows of the symmetric hit matrix are written without
-// atomics. The list is then single level (radius rc + skin) and is rebuilt from scratch each time.
-__device__ void build_small(const Dev& d, Ctx& cx) {
-  const int N = cx.N, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
+// ------------------------------------------------------------------ SMALL mode (N <= NSMALL, one atom per thread)
+// Two levels, like the large systems, but the OUTER list is the symmetric N x N hit BIT MATRIX (radius rc+skin+oskin):
+// every unordered pair is tested ONCE, 32 x 32 tile by tile, on the FP32 pipe; the warp ballot of each column gives the
+// transposed bits, so both rows of the matrix are written without atomics (word-major in global memory: coalesced,
+// 32 KB per configuration at N = 500, L1/L2 resident). It carries no periodic-image information, so it survives
+// re-wrapping and rejected moves and is rebuilt only when an atom has used up the outer displacement budget.
+__device__ void build_outer_small(const Dev& d, Ctx& cx) {
+  const int N = cx.N, Npad = cx.Npad, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double L = cx.L, rlo = d.rc + d.skin + d.oskin, invL = 1.0 / L;
   const int W = (N + 31) / 32;
-  cx.mic = L < 2.0 * rl * (1.0 + 1e-3);
   __syncthreads();
   wrap_and_refresh(cx, true);
   __syncthreads();
-  const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
-    const int ntile = W * (W + 1) / 2;
-  const bool bins = !cx.mic && rl * invL * (1.0 + 1e-3) < 0.43;     // see extract_rows_bins
-  const long long t_tiles0 = clock64();
-  if (bins) bin_masks(cx);
-  const int WS = W | 1;
+  const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
+  const int ntile = W * (W + 1) / 2;
   const uint32_t lastmask = (N & 31) ? (1u << (N & 31)) - 1u : 0xffffffffu;
   for (int t = wid; t < ntile; t += nw) {
     int ti = 0, rem = t;                      // tile (ti, tj), ti <= tj, enumerated row by row
@@ -559,11 +431,8 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
     const int tj = ti + rem;
     const int i = ti * 32 + lane;             // < Npad (Npad >= 32 W); rows >= N are never read
     const float4 pi = cx.sf[i];
-    // explicit 32-bit shared addresses: immediate offsets for the 32 broadcast loads, one add per column store
     const unsigned pj_s = (unsigned)__cvta_generic_to_shared(cx.sf + tj * 32);
-    unsigned col_s = (unsigned)__cvta_generic_to_shared(cx.hbits + (size_t)(tj * 32) * WS + ti);
-    const bool wcol = lane == 0 && ti != tj;
-    uint32_t mask = 0;
+    uint32_t mask = 0, mycol = 0;
     // fractional coordinates lie in [0,1]: the nearest-image distance along an axis is min(|d|, 1 - |d|), the same
     // value as d - rint(d) gives, in two instructions; the test is symmetric in (i, j) bit for bit
 #pragma unroll
@@ -575,18 +444,148 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
       const bool hit = fmaf(az, az, fmaf(ay, ay, ax * ax)) < rl2f;
       const uint32_t col = __ballot_sync(0xffffffffu, hit);   // column jj of the tile = row (tj*32+jj), word ti
       if (hit) mask |= 1u << jj;
-      if (wcol) sts_u32(col_s, col);
-      col_s += 4u * WS;
+      if (lane == jj) mycol = col;
     }
     if (tj == W - 1) mask &= lastmask;        // padded columns
     if (ti == tj) mask &= ~(1u << lane);      // self
-    cx.hbits[(size_t)i * WS + tj] = mask;
+    cx.hbT[(size_t)tj * Npad + i] = mask;                                  // row i, word tj
+    if (ti != tj) cx.hbT[(size_t)ti * Npad + tj * 32 + lane] = mycol;      // row tj*32+lane, word ti (rows >= N: never read)
+  }
+  const int i = threadIdx.x;
+  if (i < N) { cx.gx0o[i] = cx.sp[3 * i] * invL; cx.gx0o[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0o[2 * Npad + i] = cx.sp[3 * i + 2] * invL; }
+  __syncthreads();
+  cx.L0o = L;
+  update_thr(d, cx);
+  if (threadIdx.x == 0) cx.ct[NM_CT_OUTER_BUILDS]++;
+}
+
+// One thread's pass over its outer bit row. FOUR candidates per iteration (the next set bits of the current word; a
+// word with fewer left is topped up with the parked dummy atom, which never hits): four independent gathers and
+// distance tests in flight instead of one serial chain per candidate. Hits are pushed, predicated, into a 128-bit
+// shift register (entries XOR the dummy index, so that the zero bits of a partial quad read as the dummy atom); once
+// per iteration the four oldest entries leave as one 8-byte quad store into the [quad][atom] layout.
+template <bool GHOST>
+__device__ __forceinline__ void walk_outer_row(const Dev& d, Ctx& cx, int i, const float4 pi, float rl2f, int& over, double& tot) {
+  const int N = cx.N, Npad = cx.Npad, W = (N + 31) / 32;
+  char* lq = reinterpret_cast<char*>(cx.list + i);
+  const unsigned rowbytes = (unsigned)Npad * 8u;
+  const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf), gi_s = (unsigned)__cvta_generic_to_shared(cx.ginfo),
+                 tb_s = (unsigned)__cvta_generic_to_shared(cx.gtbl);
+  const unsigned long long dummy4 = 0x0001000100010001ull * (unsigned long long)N;
+  const uint32_t* hrow = cx.hbT + i;
+  unsigned long long hi = 0ull, lo = 0ull;
+  int fill = 0, oq = 0, cnt = 0;
+  auto emit = [&](unsigned long long quad) {
+    if (oq < d.maxq) { *reinterpret_cast<unsigned long long*>(lq) = quad ^ dummy4; lq += rowbytes; } else over = 1;
+    oq++;
+  };
+  int w = 0;
+  uint32_t m = hrow[0], mnext = W > 1 ? hrow[Npad] : 0u;            // the next word is in flight while this one is walked
+  for (;;) {
+    while (m == 0u && ++w < W) { m = mnext; mnext = w + 1 < W ? hrow[(size_t)(w + 1) * Npad] : 0u; }
+    if (w >= W) break;
+    unsigned jj[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const unsigned bit = (unsigned)__ffs(m) - 1u;                  // m == 0: bit = 0xffffffff, replaced by the dummy below
+      jj[t] = m ? 32u * (unsigned)w + bit : (unsigned)N;
+      m &= m - 1u;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const unsigned j = jj[t];
+      float4 pj;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(pj.w) : "r"(sf_s + 16u * j));
+      const float ax = fabsf(pi.x - pj.x), ay = fabsf(pi.y - pj.y), az = fabsf(pi.z - pj.z);
+      const float mx = fminf(ax, 1.f - ax), my = fminf(ay, 1.f - ay), mz = fminf(az, 1.f - az);
+      unsigned idx = j;
+      if (GHOST) {
+        const unsigned g = (ax > 0.5f ? 1u : 0u) | (ay > 0.5f ? 2u : 0u) | (az > 0.5f ? 4u : 0u);
+        const uint32_t gj = lds_u32(gi_s + 4u * j);
+        unsigned short r;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=h"(r) : "r"(tb_s + ((gj & 7u) << 3) + g));
+        idx = g ? (unsigned)Npad + (gj >> 8) + (unsigned)r - 1u : j;
+      }
+      if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < rl2f) {              // predicated push from the top
+        lo = (lo >> 16) | (hi << 48);
+        hi = (hi >> 16) | ((unsigned long long)(idx ^ (unsigned)N) << 48);
+        fill++; cnt++;
+      }
+    }
+    if (fill >= 4) {                                                 // the four oldest entries start 16*fill bits from the top
+      const int sh = 16 * fill - 64;                                 // 0, 16, 32 or 48
+      emit(sh ? (hi << sh) | (lo >> (64 - sh)) : hi);
+      fill -= 4;
+    }
+  }
+  if (fill) emit(hi >> (64 - 16 * fill));
+  cx.nnb[i] = (uint16_t)min(oq, d.maxq);
+  tot = (double)cnt;
+  const double invL = 1.0 / cx.L;
+  cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+}
+
+// INNER list (radius rl = rc + skin) = the outer candidates currently within rl. The owner of row i walks the set bits
+// of its outer row (flattened walk: every lane advances through ITS candidates, so a warp iterates max(candidates)
+// times), tests the float32 nearest-image distance and stores the index of the copy to use -- the atom itself, or its
+// ghost shifted along the axes where the pair wraps (|d| > 1/2 of the box) -- straight into the [quad][atom] layout.
+// No image codes, no groups: the only padding is the last quad. Atoms are re-wrapped here, and the ghost table is
+// rebuilt: atom j gets a copy for every non-empty subset of the faces it is within rl (1 + 1e-3) of.
+// Boxes below 2 rl (or more ghosts than the shared array holds, or FP32 mode) use plain indices and the per-pair
+// minimum image (cx.mic).
+__device__ void build_inner_small(const Dev& d, Ctx& cx) {
+  const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
+  const int W = (N + 31) / 32;
+  __syncthreads();
+  wrap_and_refresh(cx, true);
+  __syncthreads();
+  const bool own = tid < N;
+  const float rg = (float)(rl * invL * (1.0 + 1e-3));
+  float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned nb = 0, hb = 0;
+  if (own) {
+    pi = cx.sf[tid];
+    hb = (pi.x < 0.5f ? 1u : 0u) | (pi.y < 0.5f ? 2u : 0u) | (pi.z < 0.5f ? 4u : 0u);
+    nb = ((hb & 1u) ? pi.x < rg : pi.x > 1.f - rg) ? 1u : 0u;
+    nb |= ((hb & 2u) ? pi.y < rg : pi.y > 1.f - rg) ? 2u : 0u;
+    nb |= ((hb & 4u) ? pi.z < rg : pi.z > 1.f - rg) ? 4u : 0u;
+  }
+  // exclusive block scan of the ghost counts
+  const int cnt = own ? (1 << __popc(nb)) - 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) cx.iscan[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const int v = lane < nw ? cx.iscan[lane] : 0;
+    int w = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    cx.iscan[lane] = w - v;                               // exclusive prefix of the warp totals
+    if (lane == 31) cx.iscan[32] = w;                     // number of ghosts
   }
   __syncthreads();
-  if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t_tiles0);
-  const int over = bins ? extract_rows_bins(d, cx) : extract_rows_small(d, cx);
-  if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
-  cx.L0 = L; cx.L0o = L;
+  const int base = cx.iscan[wid] + incl - cnt, nghost = cx.iscan[32];
+  cx.mic = d.f32 || L < 2.0 * rl * (1.0 + 1e-3) || nghost > ghost_cap(N);
+  cx.ghost = !cx.mic;
+  const bool ghost = cx.ghost;
+  if (own) {
+    const uint32_t gi = ghost ? ((uint32_t)base << 8) | (hb << 3) | nb : 0u;
+    cx.ginfo[tid] = gi;
+    cx.ginfo_g[(size_t)cx.lbuf * Npad + tid] = gi;
+    if (ghost) write_ghosts(cx, tid, cx.sp[3 * tid], cx.sp[3 * tid + 1], cx.sp[3 * tid + 2]);
+  }
+  __syncthreads();
+  const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
+  int over = 0; double tot = 0.0;
+  if (own) { if (ghost) walk_outer_row<true>(d, cx, tid, pi, rl2f, over, tot); else walk_outer_row<false>(d, cx, tid, pi, rl2f, over, tot); }
+  double r[2] = { tot, (double)over };
+  bsum<2>(r, cx);
+  cx.list_pairs = 0.5 * r[0];
+  if (r[1] > 0.0) cx.status |= ST_NEIGH;
+  cx.L0 = L;
   update_thr(d, cx);
 }
 
@@ -744,25 +743,25 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
 __device__ void build_list(const Dev& d, Ctx& cx) {
   const long long t_build0 = clock64();
   if (cx.in_move && cx.lbuf == cx.sv_lbuf) { cx.lbuf ^= 1; select_list(cx); }   // keep the list of the saved positions
-  if (d.small) {
-    build_small(d, cx);
-    if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; const unsigned long long dt = (unsigned long long)(clock64() - t_build0); cx.ct[NM_CT_CLK_BUILD] += dt; cx.ct[NM_CT_CLK_INNER] += dt; }
-    return;
-  }
   int flag = cx.thro2 < 0.0;
   if (!flag) {
     const double invL = 1.0 / cx.L;
     for (int i = threadIdx.x; i < cx.N; i += blockDim.x)
       flag |= disp2o(cx, i, cx.sp[3 * i], cx.sp[3 * i + 1], cx.sp[3 * i + 2], invL) > cx.thro2;
   }
-  if (__syncthreads_or(flag)) { const long long t0 = clock64(); cx.outer_in_move = cx.in_move; build_outer(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t0); }
-  { const long long t0 = clock64(); build_inner(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_INNER] += (unsigned long long)(clock64() - t0); }
+  if (__syncthreads_or(flag)) {
+    const long long t0 = clock64();
+    if (d.small) build_outer_small(d, cx);                    // the bit matrix carries no images: it survives a rejected move
+    else { cx.outer_in_move = cx.in_move; build_outer(d, cx); }
+    if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t0);
+  }
+  { const long long t0 = clock64(); if (d.small) build_inner_small(d, cx); else build_inner(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_INNER] += (unsigned long long)(clock64() - t0); }
   if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; cx.ct[NM_CT_CLK_BUILD] += (unsigned long long)(clock64() - t_build0); }
 }
 
 // barrier after a position update; rebuilds the list if any thread saw its budget exceeded
 __device__ __forceinline__ void sync_and_maybe_build(const Dev& d, Ctx& cx, int flag) {
-  if (threadIdx.x < 27) {                  // image shift vectors k*L of the current box (readers are past a barrier)
+  if (!d.small && threadIdx.x < 27) {      // image shift vectors k*L of the current box (readers are past a barrier)
     const int c = threadIdx.x;
     cx.sht[3 * c] = (c / 9 - 1) * cx.L; cx.sht[3 * c + 1] = ((c / 3) % 3 - 1) * cx.L; cx.sht[3 * c + 2] = (c % 3 - 1) * cx.L;
   }
@@ -840,8 +839,11 @@ __device__ __forceinline__ void lj_pair(double xj, double yj, double zj, double 
 // EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
 // half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
 // Ends with a barrier: shared positions may be rewritten afterwards.
-template <bool EW, bool KICK, bool MIC, bool S32>
+// IMG: how a list entry names the periodic image of its atom. 0: one image code per quad (LARGE mode), 1: per-pair
+// minimum image (small boxes), 2: the entry is the index of the copy to use (SMALL mode ghost atoms: nothing to do).
+template <bool EW, bool KICK, int IMG, bool S32>
 __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
+  constexpr bool MIC = IMG == 1;
   const int N = cx.N, Npad = cx.Npad;
   const long long rc2_bits = __double_as_longlong(d.rc * d.rc);
   const int L_hi = __double2hiint(cx.L), L_lo = __double2loint(cx.L), hL_hi = __double2hiint(0.5 * cx.L);
@@ -864,20 +866,20 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // for the next iteration
       lp += stride;
       double xs = xi, ys = yi, zs = zi;
-      if (!MIC) {
+      if (IMG == 0) {
         const unsigned code = ((cur.x >> 13) & 7u) | ((cur.x >> 26) & 0x38u);
         const double* sh = cx.sht + 3 * code;
         xs -= sh[0]; ys -= sh[1]; zs -= sh[2];
       }
       // explicit 32-bit shared addresses (one IMAD per neighbour). ptxas places each gather next to its use
       // whatever the source order (volatile loads up front were tried: same schedule)
-      const unsigned a0 = sp_s + 24u * (cur.x & 0x1fffu), a1 = sp_s + 24u * ((cur.x >> 16) & 0x1fffu),
+      const unsigned a0 = sp_s + 24u * (IMG == 0 ? cur.x & 0x1fffu : cur.x & 0xffffu), a1 = sp_s + 24u * (IMG == 0 ? (cur.x >> 16) & 0x1fffu : cur.x >> 16),
                      a2 = sp_s + 24u * (cur.y & 0xffffu), a3 = sp_s + 24u * (cur.y >> 16);
       double p[12];
 #ifdef NM_PLAIN_GATHER
-      { const double *q0 = cx.sp + 3 * (cur.x & 0x1fffu), *q1 = cx.sp + 3 * ((cur.x >> 16) & 0x1fffu), *q2 = cx.sp + 3 * (cur.y & 0xffffu), *q3 = cx.sp + 3 * (cur.y >> 16);
+      { const double *q0 = cx.sp + (a0 - sp_s) / 8u, *q1 = cx.sp + (a1 - sp_s) / 8u, *q2 = cx.sp + (a2 - sp_s) / 8u, *q3 = cx.sp + (a3 - sp_s) / 8u;
         p[0] = q0[0]; p[1] = q0[1]; p[2] = q0[2]; p[3] = q1[0]; p[4] = q1[1]; p[5] = q1[2];
-        p[6] = q2[0]; p[7] = q2[1]; p[8] = q2[2]; p[9] = q3[0]; p[10] = q3[1]; p[11] = q3[2]; (void)a0; (void)a1; (void)a2; (void)a3; }
+        p[6] = q2[0]; p[7] = q2[1]; p[8] = q2[2]; p[9] = q3[0]; p[10] = q3[1]; p[11] = q3[2]; }
 #else
       lds_f64x3(a0, p[0], p[1], p[2]); lds_f64x3(a1, p[3], p[4], p[5]); lds_f64x3(a2, p[6], p[7], p[8]); lds_f64x3(a3, p[9], p[10], p[11]);
 #endif
@@ -946,7 +948,7 @@ __device__ void eval_forces_f32(const Dev& d, Ctx& cx, double dtf, double (&out)
         const float4 pj = cx.sf[jj[t]];
         float dx = xs - pj.x, dy = ys - pj.y, dz = zs - pj.z;
         if (MIC) { dx -= __fadd_rn(__fadd_rn(dx, magic), -magic); dy -= __fadd_rn(__fadd_rn(dy, magic), -magic); dz -= __fadd_rn(__fadd_rn(dz, magic), -magic); }
-        const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) * L2f;
+        const float rsq = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, pj.w))) * L2f;
         const bool in = rsq < rc2f;
         const float r2inv = __frcp_rn(rsq);
         const float r6inv = r2inv * r2inv * r2inv;
@@ -983,13 +985,15 @@ __device__ void eval_forces_f32(const Dev& d, Ctx& cx, double dtf, double (&out)
   }
 }
 
+// S32 marks the 1024-thread kernels: the only ones that can meet a LARGE system (N > NSMALL)
 template <bool EW, bool KICK, bool S32>
 __device__ __forceinline__ void eval_forces(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
   if (d.f32) {
-    if (cx.mic) eval_forces_f32<EW, KICK, true>(d, cx, dtf, out);
+    if (cx.mic) eval_forces_f32<EW, KICK, true>(d, cx, dtf, out);           // SMALL mode: always (no float ghost copies)
     else eval_forces_f32<EW, KICK, false>(d, cx, dtf, out);
-  } else if (cx.mic) eval_forces_t<EW, KICK, true, S32>(d, cx, dtf, out);
-  else eval_forces_t<EW, KICK, false, S32>(d, cx, dtf, out);
+  } else if (cx.mic) eval_forces_t<EW, KICK, 1, S32>(d, cx, dtf, out);
+  else if (!S32 || d.small) eval_forces_t<EW, KICK, 2, S32>(d, cx, dtf, out);
+  else eval_forces_t<EW, KICK, 0, S32>(d, cx, dtf, out);
 }
 
 // the acceptance rule shared by all moves (lammps_remcmc.py:487-500, 532-547, 578-593, 623-638)
@@ -1028,14 +1032,16 @@ __device__ void restore_xf(const Dev& d, Ctx& cx, bool with_v) {
     cx.lbuf = cx.sv_lbuf; select_list(cx);
     cx.L0 = cx.sv_L0; cx.mic = cx.sv_mic; cx.list_pairs = cx.sv_list_pairs;
     if (cx.outer_in_move) cx.L0o = -1.0;
+    cx.ghost = d.small && !cx.mic && cx.L0 > 0.0;
+    if (cx.ghost) load_ginfo(cx);                 // thread i reloads entry i and is its only reader until the next build
   }
   cx.in_move = 0;
   update_thr(d, cx);
   for (int i = threadIdx.x; i < cx.N; i += blockDim.x) {
+    store_pos(cx, i, cx.gxs[i], cx.gxs[cx.Npad + i], cx.gxs[2 * cx.Npad + i]);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       const int o = a * cx.Npad + i;
-      cx.sp[3 * i + a] = cx.gxs[o];
       cx.gf[o] = cx.gfs[o];
       if (with_v) cx.gv[o] = cx.gvs[o];
     }
@@ -1054,7 +1060,7 @@ __device__ void bulk_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
     double u[3]; rng_uniform3(r, (uint32_t)i, P_BULK_DISP, u);
     const double x = cx.sp[3 * i] + dmax * 2.0 * (u[0] - 0.5), y = cx.sp[3 * i + 1] + dmax * 2.0 * (u[1] - 0.5),
                  z = cx.sp[3 * i + 2] + dmax * 2.0 * (u[2] - 0.5);
-    cx.sp[3 * (i)] = x; cx.sp[3 * (i) + 1] = y; cx.sp[3 * (i) + 2] = z;
+    store_pos(cx, i, x, y, z);
     if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
   }
   sync_and_maybe_build(d, cx, flag);
@@ -1096,7 +1102,7 @@ __device__ void volume_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double
       // an atom represented k boxes away from [0,L) must land on the same lattice image, hence the k*(boxnew-Lnew)
       const double kx = floor(cx.sp[3 * i] * invLold), ky = floor(cx.sp[3 * i + 1] * invLold), kz = floor(cx.sp[3 * i + 2] * invLold);
       const double x = scale * cx.sp[3 * i] - kx * dround, y = scale * cx.sp[3 * i + 1] - ky * dround, z = scale * cx.sp[3 * i + 2] - kz * dround;
-      cx.sp[3 * (i)] = x; cx.sp[3 * (i) + 1] = y; cx.sp[3 * (i) + 2] = z;
+      store_pos(cx, i, x, y, z);
       if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
     }
     sync_and_maybe_build(d, cx, flag);
@@ -1264,7 +1270,7 @@ __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, d
                    vz = fma(dtf, cx.gf[2 * Npad + i], cx.gv[2 * Npad + i]);
       cx.gv[i] = vx; cx.gv[Npad + i] = vy; cx.gv[2 * Npad + i] = vz;
       const double x = fma(dt, vx, cx.sp[3 * i]), y = fma(dt, vy, cx.sp[3 * i + 1]), z = fma(dt, vz, cx.sp[3 * i + 2]);
-      cx.sp[3 * (i)] = x; cx.sp[3 * (i) + 1] = y; cx.sp[3 * (i) + 2] = z;
+      store_pos(cx, i, x, y, z);
       if (!flag) flag = disp2(cx, i, x, y, z, invL) > cx.thr2;
     }
     sync_and_maybe_build(d, cx, flag);
@@ -1368,7 +1374,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
         if (acc) {
           nacc++; en.pe += de;
           __syncwarp();
-          if (lane == 0) { cx.sp[3 * kk] = xn; cx.sp[3 * kk + 1] = yn; cx.sp[3 * kk + 2] = zn; }
+          if (lane == 0) store_pos(cx, kk, xn, yn, zn);
           __syncwarp();
           umax = fmax(umax, un);
         }
@@ -1759,7 +1765,9 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   // default skin: tuned at the stationary state of the default workload (step sizes adapted to 50 % acceptance, 1.6
   // rebuilds per move): 0.4 where a rebuild costs 3 evaluations (hit-matrix builds), 0.3 with the cheaper two-level lists
   d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : 0.3);
-  d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 1.3;        // stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6
+  // outer skin. LARGE: stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6. SMALL: the outer list is a
+  // bit matrix, its radius only sets how many candidates an inner build walks and how often the tile pass runs
+  d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : (N <= NSMALL ? 0.6 : 1.3);
   d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);
   {
     // list capacities: neighbours inside the list radius at the densest state we expect (rho* 1.6) plus slack,
@@ -1780,11 +1788,12 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   d.small = N <= NSMALL;
   h->smem = smem_bytes(d.Npad, N, d.small, h->threads);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, cfg->device) == cudaSuccess) h->nsm = pr.multiProcessorCount; else h->nsm = 148; }
-  d.nsm = h->nsm; d.per_sm = (h->smem * 2 <= 220 * 1024 && h->threads <= 512) ? 2 : 1;
+  d.nsm = h->nsm; d.per_sm = ((h->smem + 1024) * 2 <= 227 * 1024 && h->threads <= 512) ? 2 : 1;
   if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
   const size_t per = (size_t)nrep * 3 * d.Npad;
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, 2 * per);
-  DA(d.list, ((size_t)nrep * 2 * (d.maxq + 1) + 2) * d.Npad); DA(d.lcur, nrep);       // one spare row per buffer: the loop prefetches one quad ahead
+  DA(d.list, ((size_t)nrep * 2 * (d.maxq + 1) + 2) * d.Npad); DA(d.lcur, nrep);
+  if (d.small) { DA(d.hbT, (size_t)nrep * (d.Npad / 32) * d.Npad); DA(d.ginfo, (size_t)nrep * 2 * d.Npad); }       // one spare row per buffer: the loop prefetches one quad ahead
   DA(d.ltmp, (size_t)nrep * ((d.maxnbo + 3) & ~3) * d.Npad); DA(d.nnb, (size_t)nrep * 2 * d.Npad); DA(d.micmode, nrep);
   DA(d.olist, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.ocode, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.onq, (size_t)nrep * d.Npad);
   DA(d.x0o, per); DA(d.L0o, nrep);
