@@ -12,7 +12,9 @@
  *     nm_last_error() returns a thread-local message for the last failure.
  *   - "slot" k = i*NT + j is the reference's replica index (pressure i,
  *     temperature j, C order; lammps_remcmc.py:117,300). Host-visible arrays
- *     are always in LOCAL SLOT order (slot_local = k - rep_offset).
+ *     are always in LOCAL SLOT order: local pressure row lr holds the NT slots of global
+ *     row rep_offset/NT + lr*row_stride (row_stride 1: a contiguous block of rows,
+ *     slot_local = k - rep_offset; row_stride G with rep_offset = rank*NT: row u -> rank u mod G).
  *   - positions/velocities: double[n_rep][3*natoms], atom-id major (x0 y0 z0 x1 ..),
  *     the layout of lammps.gather_atoms('x',1,3) (lammps_remcmc.py:381-382).
  *   - host pointers are caller-owned (NumPy arrays); device memory is owned by
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NM_ABI_VERSION 1
+#define NM_ABI_VERSION 2
 
 /* error codes */
 #define NM_OK         0
@@ -100,6 +102,9 @@ typedef struct nm_config {
   int32_t  text_rounding;   /* 1: reproduce the '%f' (6-decimal) rounding the reference
                                applies to every value it passes to LAMMPS as text
                                (timestep, box side, bulk displacement, velocity T)     */
+  int32_t  row_stride;      /* global pressure rows between consecutive local rows; <= 1 = contiguous block.
+                               G ranks, cyclic: rep_offset = rank*nt, row_stride = G        */
+  int32_t  reserved0;       /* set to 0                                                    */
   double   ppos, pvol;      /* PPOS, PVOL move probabilities (-pm, -vm)                    */
   double   lat_scale;       /* LAT[EL][1] (1.122): displacement scale factor               */
   double   mass;            /* MASS[EL]                                                    */
@@ -155,27 +160,32 @@ int  nm_get_thermo(nm_engine* h, double* out);
 /* ---- a-10: gen_mc_param (lammps_remcmc.py:726-745): adapt dx, dv, dt; zero counters */
 int  nm_adapt(nm_engine* h);
 
-/* ---- a-11: replica_exchange (lammps_remcmc.py:776-803).
+/* ---- a-11: replica_exchange (lammps_remcmc.py:776-803). Exchanges never cross pressure rows
+ *      (:782-789) and an engine holds whole rows, so every engine decides the swaps of ITS rows
+ *      from its own (pe+ke, vol) values: no collective sits on the critical path. et / pf are the
+ *      labels of nm_set_labels; the uniform of row u's n-th pair is draw u*NT*(NT-1)/2 + n of the
+ *      job-wide stream whatever the row -> rank map.
+ *   nm_exchange      : pack + sweep of the local rows + permutation of the local
+ *                      slot -> configuration labels (configurations never move).
+ *                      uniforms: optional HOST array of NP*NT*(NT-1)/2 doubles in GLOBAL draw
+ *                      order (injects the reference's np.random stream); NULL = the engine's
+ *                      counter-based stream for this cycle.
+ *                      perm_out: optional HOST int32[n_rep]; perm_out[k] = local slot whose
+ *                      pre-exchange configuration now sits in local slot k.
+ *                      swaps_out: optional HOST int64, accepted swaps of the local rows.
+ *                      With both NULL the call is asynchronous on the stream.
  *   nm_exchange_pack : writes (pe+ke, vol) of every local slot to a DEVICE buffer
- *                      double[n_rep][2] (the NCCL all-gather payload).
- *   nm_exchange_apply: given the all-gathered DEVICE table double[n_rep_global][2]
- *                      (slot order), replays the sequential sweep of every pressure row
- *                      and permutes the slot->configuration labels of the local rows.
- *                      uniforms: optional HOST array of NP*NT*(NT-1)/2 doubles in draw
- *                      order (injects the reference's np.random stream); NULL = the
- *                      engine's counter-based stream for this cycle.
- *                      et_global, pf_global: HOST arrays [n_rep_global] (CONST of all slots).
- *                      perm_out: optional HOST int32[n_rep_global]; perm_out[k] = slot whose
- *                      pre-exchange configuration now sits in slot k.
- *                      swaps_out: optional HOST int64, number of accepted swaps (global).
- *   nm_exchange      : single-rank convenience = pack + apply on the local table. */
-int  nm_exchange_pack(nm_engine* h, void* dev_dst);
-int  nm_exchange_apply(nm_engine* h, const void* dev_table_global,
-                       const double* et_global, const double* pf_global,
-                       const double* uniforms, int64_t cycle,
-                       int32_t* perm_out, int64_t* swaps_out);
+ *                      double[n_rep][2]: the payload of the NCCL all-gather that gives every
+ *                      rank (and the log) the job-wide table, as the reference's client holds it.
+ *   nm_exchange_apply: the same sweep of the local rows, reading a job-wide DEVICE table
+ *                      double[n_rep_global][2] in GLOBAL slot order (an all-gathered table, or
+ *                      one injected by a test) instead of the local pack. */
 int  nm_exchange(nm_engine* h, const double* uniforms, int64_t cycle,
                  int32_t* perm_out, int64_t* swaps_out);
+int  nm_exchange_pack(nm_engine* h, void* dev_dst);
+int  nm_exchange_apply(nm_engine* h, const void* dev_table_global,
+                       const double* uniforms, int64_t cycle,
+                       int32_t* perm_out, int64_t* swaps_out);
 
 /* counters (for the roofline figures): out[NM_COUNTER_WIDTH] */
 int  nm_get_counters(nm_engine* h, uint64_t* out);

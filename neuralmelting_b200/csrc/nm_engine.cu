@@ -18,8 +18,16 @@
 #include "nm_b200.h"
 #include "nm_device.cuh"
 
+#ifndef NM_UNR
+#define NM_UNR 1
+#endif
+#ifndef NM_CTAS_PER_SM
+#define NM_CTAS_PER_SM(T) (1024 / (T))
+#endif
+
 namespace nm {
 
+constexpr int LIST_SPARE_ROWS = 4;       // rows past the last quad of a list buffer that the force loop may prefetch
 constexpr int NCMAX = 10;                // cell grid is at most 10^3 (N = 4000 must stay below the 196 KB shared-memory carve-out: L1 keeps 60 KB)
 constexpr int RED_HALF = 32 * 9;           // one block_sum scratch area (K <= 9)
 constexpr int RED_DOUBLES = 2 * RED_HALF;
@@ -36,6 +44,7 @@ constexpr int ST_BOX = 1, ST_NEIGH = 2;  // status bits
 // ------------------------------------------------------------------ device-side engine description
 struct Dev {
   int N, Npad, nrep, nrep_global, rep_offset, nt, maxq, maxqo, maxnbo;   // inner / outer list capacity in quads, outer scratch entries
+  int row0, row_stride;                    // local pressure row lr is global row row0 + lr * row_stride (row u -> rank u mod G: row0 = rank, stride = G)
   int nstps, mod, bulk, text_rounding;
   int nsm, per_sm;                         // SM count and CTAs that fit per SM (cost-balanced placement)
   int f32;                                 // precision = 32: pair arithmetic in FP32 on the fractional float copies
@@ -76,6 +85,10 @@ struct Dev {
   unsigned long long* counters;            // [NM_COUNTER_WIDTH]
 };
 
+// global slot index k = i*NT + j of local slot k_local (the RNG streams and the exchange draws are keyed on it, so results
+// do not depend on how the pressure rows are spread over GPUs)
+__host__ __device__ inline int gslot(const Dev& d, int k) { return (d.row0 + (k / d.nt) * d.row_stride) * d.nt + k % d.nt; }
+
 // per-CTA context (registers + shared-memory carve)
 struct Ctx {
   int N, Npad, c;
@@ -86,6 +99,7 @@ struct Ctx {
   uint32_t* ginfo;              // shared (SMALL mode): ghost table of the current list, one word per atom
   uint32_t* ginfo_g;            // global copies of the ghost table, one per list buffer
   uint8_t* gtbl;                // shared (SMALL mode): rank of image subset g among the subsets of a near-face mask, [8][8]
+  uint16_t* gidx;               // shared (SMALL mode): [Npad][8] index of the copy of atom j for image subset g (g = 0: j itself)
   int* iscan;                   // shared: block-scan scratch (34 ints)
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
@@ -119,8 +133,8 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
   if (small) b += sizeof(double) * 3 * (size_t)ghost_cap(N);
   b += sizeof(unsigned long long) * (2 + NM_COUNTER_WIDTH);
   b += sizeof(float4) * (size_t)Npad;
-  b += sizeof(int) * (8 + 2 + 34);                              // ibc, iscan
-  if (small) b += sizeof(uint32_t) * (size_t)Npad + 64;         // ghost table, subset-rank table
+  b += sizeof(int) * (8 + 2 + 34);                              // ibc, iscan (44 ints: keeps 16-byte alignment)
+  if (small) b += sizeof(uint32_t) * (size_t)Npad + 64 + sizeof(uint16_t) * 8 * (size_t)Npad;   // ghost table, subset-rank table, copy index table
   else {
     b += sizeof(int) * 2 * (NCMAX * NCMAX * NCMAX + 1);         // cell counts / starts
     b += sizeof(uint16_t) * (size_t)Npad;                       // cell members
@@ -162,6 +176,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.ibc = q; q += 8 + 2;
   cx.iscan = q; q += 34;
   if (d.small) {
+    cx.gidx = reinterpret_cast<uint16_t*>(q); q += 4 * d.Npad;        // first: 16-byte aligned rows
     cx.ginfo = reinterpret_cast<uint32_t*>(q); q += d.Npad;
     cx.gtbl = reinterpret_cast<uint8_t*>(q);
     cx.cell_cnt = cx.cell_start = nullptr; cx.cell_atoms = nullptr; cx.gcur = nullptr;
@@ -177,14 +192,14 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
     cx.cell_start = q; q += NCMAX * NCMAX * NCMAX + 1;
     cx.cell_atoms = reinterpret_cast<uint16_t*>(q);
     cx.gcur = cx.cell_atoms + d.Npad;
-    cx.ginfo = nullptr; cx.gtbl = nullptr;
+    cx.ginfo = nullptr; cx.gtbl = nullptr; cx.gidx = nullptr;
   }
   cx.hbT = d.small ? d.hbT + (size_t)c * (d.Npad / 32) * d.Npad : nullptr;
   cx.ginfo_g = d.small ? d.ginfo + (size_t)c * 2 * d.Npad : nullptr;
   const size_t off = (size_t)c * 3 * d.Npad;
   cx.gx = d.x + off; cx.gv = d.v + off; cx.gf = d.f + off;
   cx.gxs = d.xs + off; cx.gvs = d.vs + off; cx.gfs = d.fs + off;
-  cx.list_stride = (size_t)(d.maxq + 1) * d.Npad;
+  cx.list_stride = (size_t)(d.maxq + LIST_SPARE_ROWS) * d.Npad;
   cx.list_base = d.list + (size_t)c * 2 * cx.list_stride;
   cx.nnb_base = d.nnb + (size_t)c * 2 * d.Npad;
   cx.gx0_base = d.x0 + 2 * off;
@@ -410,19 +425,80 @@ __device__ void wrap_and_refresh(Ctx& cx, bool wrap) {
 }
 
 // ------------------------------------------------------------------ SMALL mode (N <= NSMALL, one atom per thread)
-// Two levels, like the large systems, but the OUTER list is the symmetric N x N hit BIT MATRIX (radius rc+skin+oskin):
-// every unordered pair is tested ONCE, 32 x 32 tile by tile, on the FP32 pipe; the warp ballot of each column gives the
-// transposed bits, so both rows of the matrix are written without atomics (word-major in global memory: coalesced,
-// 32 KB per configuration at N = 500, L1/L2 resident). It carries no periodic-image information, so it survives
-// re-wrapping and rejected moves and is rebuilt only when an atom has used up the outer displacement budget.
-__device__ void build_outer_small(const Dev& d, Ctx& cx) {
-  const int N = cx.N, Npad = cx.Npad, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const double L = cx.L, rlo = d.rc + d.skin + d.oskin, invL = 1.0 / L;
+// Single-level list (radius rl = rc + skin), rebuilt from scratch each time in two steps.
+// (1) Symmetric N x N hit BIT MATRIX: every unordered pair is tested ONCE, 32 x 32 tile by tile, on the FP32 pipe
+//     (0.7 instructions per pair test); the warp ballot of each column gives the transposed bits, so both rows of the
+//     matrix are written without atomics (word-major in global memory: coalesced, 32 KB per configuration at N = 500).
+// (2) Every thread walks the set bits of its row, four per iteration (four independent gathers in flight), and stores
+//     for each the index of the COPY to use -- the atom itself, or its ghost shifted along the axes where the pair
+//     wraps (|d| > 1/2 of the box) -- straight into the [quad][atom] layout. No image codes, no groups: the only
+//     padding is the last quad.
+// Atoms are re-wrapped here, and the ghost table is rebuilt: atom j gets a copy for every non-empty subset of the
+// faces it is within rl (1 + 1e-3) of. Boxes below 2 rl (or more ghosts than the shared array holds, or FP32 mode)
+// use plain indices and the per-pair minimum image (cx.mic).
+template <bool GHOST>
+__device__ __forceinline__ void walk_hit_row(const Dev& d, Ctx& cx, int i, const float4 pi, int& over, double& tot) {
+  const int N = cx.N, Npad = cx.Npad, W = (N + 31) / 32;
+  char* li = reinterpret_cast<char*>(cx.list + i);
+  const unsigned rowbytes = (unsigned)Npad * 8u, cap = 4u * (unsigned)d.maxq;
+  const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf), gx_s = (unsigned)__cvta_generic_to_shared(cx.gidx);
+  const uint32_t* hrow = cx.hbT + i;
+  unsigned pos = 0;
+  int w = 0;
+  uint32_t m = hrow[0], mnext = W > 1 ? hrow[Npad] : 0u;            // the next word is in flight while this one is walked
+  for (;;) {
+    while (m == 0u && ++w < W) { m = mnext; mnext = w + 1 < W ? hrow[(size_t)(w + 1) * Npad] : 0u; }
+    if (w >= W) break;
+    const unsigned nv = min(4u, (unsigned)__popc(m));
+    unsigned jj[4], idx[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const unsigned bit = (unsigned)__ffs(m) - 1u;                  // m == 0: replaced by the parked dummy atom
+      jj[t] = m ? 32u * (unsigned)w + bit : (unsigned)N;
+      m &= m - 1u;
+    }
+    if (GHOST) {
+      float4 pj[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pj[t].x), "=f"(pj[t].y), "=f"(pj[t].z), "=f"(pj[t].w) : "r"(sf_s + 16u * jj[t]));
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        // the pair wraps along an axis <=> the fractional separation exceeds 1/2 (listed pairs: < rl/L or > 1 - rl/L)
+        const unsigned g = (fabsf(pi.x - pj[t].x) > 0.5f ? 2u : 0u) + (fabsf(pi.y - pj[t].y) > 0.5f ? 4u : 0u) + (fabsf(pi.z - pj[t].z) > 0.5f ? 8u : 0u);
+        unsigned short r;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(gx_s + 16u * jj[t] + g));
+        idx[t] = r;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 4; t++) idx[t] = jj[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const unsigned q = pos + (unsigned)t;
+      if ((unsigned)t < nv && q < cap) *reinterpret_cast<uint16_t*>(li + (q >> 2) * rowbytes + (q & 3u) * 2u) = (uint16_t)idx[t];
+    }
+    pos += nv;
+  }
+  tot = (double)pos;
+  if (pos > cap) { over = 1; pos = cap; }
+  for (; pos & 3u; pos++) *reinterpret_cast<uint16_t*>(li + (pos >> 2) * rowbytes + (pos & 3u) * 2u) = (uint16_t)N;   // dummy padding
+  cx.nnb[i] = (uint16_t)(pos >> 2);
+  const double invL = 1.0 / cx.L;
+  cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
+}
+
+__device__ void build_small(const Dev& d, Ctx& cx) {
+  const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
   const int W = (N + 31) / 32;
   __syncthreads();
   wrap_and_refresh(cx, true);
   __syncthreads();
-  const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
+  // ---- (1) tiles
+  const long long t_tiles0 = clock64();
+  const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
   const int ntile = W * (W + 1) / 2;
   const uint32_t lastmask = (N & 31) ? (1u << (N & 31)) - 1u : 0xffffffffu;
   for (int t = wid; t < ntile; t += nw) {
@@ -451,95 +527,7 @@ __device__ void build_outer_small(const Dev& d, Ctx& cx) {
     cx.hbT[(size_t)tj * Npad + i] = mask;                                  // row i, word tj
     if (ti != tj) cx.hbT[(size_t)ti * Npad + tj * 32 + lane] = mycol;      // row tj*32+lane, word ti (rows >= N: never read)
   }
-  const int i = threadIdx.x;
-  if (i < N) { cx.gx0o[i] = cx.sp[3 * i] * invL; cx.gx0o[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0o[2 * Npad + i] = cx.sp[3 * i + 2] * invL; }
-  __syncthreads();
-  cx.L0o = L;
-  update_thr(d, cx);
-  if (threadIdx.x == 0) cx.ct[NM_CT_OUTER_BUILDS]++;
-}
-
-// One thread's pass over its outer bit row. FOUR candidates per iteration (the next set bits of the current word; a
-// word with fewer left is topped up with the parked dummy atom, which never hits): four independent gathers and
-// distance tests in flight instead of one serial chain per candidate. Hits are pushed, predicated, into a 128-bit
-// shift register (entries XOR the dummy index, so that the zero bits of a partial quad read as the dummy atom); once
-// per iteration the four oldest entries leave as one 8-byte quad store into the [quad][atom] layout.
-template <bool GHOST>
-__device__ __forceinline__ void walk_outer_row(const Dev& d, Ctx& cx, int i, const float4 pi, float rl2f, int& over, double& tot) {
-  const int N = cx.N, Npad = cx.Npad, W = (N + 31) / 32;
-  char* lq = reinterpret_cast<char*>(cx.list + i);
-  const unsigned rowbytes = (unsigned)Npad * 8u;
-  const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf), gi_s = (unsigned)__cvta_generic_to_shared(cx.ginfo),
-                 tb_s = (unsigned)__cvta_generic_to_shared(cx.gtbl);
-  const unsigned long long dummy4 = 0x0001000100010001ull * (unsigned long long)N;
-  const uint32_t* hrow = cx.hbT + i;
-  unsigned long long hi = 0ull, lo = 0ull;
-  int fill = 0, oq = 0, cnt = 0;
-  auto emit = [&](unsigned long long quad) {
-    if (oq < d.maxq) { *reinterpret_cast<unsigned long long*>(lq) = quad ^ dummy4; lq += rowbytes; } else over = 1;
-    oq++;
-  };
-  int w = 0;
-  uint32_t m = hrow[0], mnext = W > 1 ? hrow[Npad] : 0u;            // the next word is in flight while this one is walked
-  for (;;) {
-    while (m == 0u && ++w < W) { m = mnext; mnext = w + 1 < W ? hrow[(size_t)(w + 1) * Npad] : 0u; }
-    if (w >= W) break;
-    unsigned jj[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const unsigned bit = (unsigned)__ffs(m) - 1u;                  // m == 0: bit = 0xffffffff, replaced by the dummy below
-      jj[t] = m ? 32u * (unsigned)w + bit : (unsigned)N;
-      m &= m - 1u;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const unsigned j = jj[t];
-      float4 pj;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(pj.w) : "r"(sf_s + 16u * j));
-      const float ax = fabsf(pi.x - pj.x), ay = fabsf(pi.y - pj.y), az = fabsf(pi.z - pj.z);
-      const float mx = fminf(ax, 1.f - ax), my = fminf(ay, 1.f - ay), mz = fminf(az, 1.f - az);
-      unsigned idx = j;
-      if (GHOST) {
-        const unsigned g = (ax > 0.5f ? 1u : 0u) | (ay > 0.5f ? 2u : 0u) | (az > 0.5f ? 4u : 0u);
-        const uint32_t gj = lds_u32(gi_s + 4u * j);
-        unsigned short r;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=h"(r) : "r"(tb_s + ((gj & 7u) << 3) + g));
-        idx = g ? (unsigned)Npad + (gj >> 8) + (unsigned)r - 1u : j;
-      }
-      if (fmaf(mz, mz, fmaf(my, my, mx * mx)) < rl2f) {              // predicated push from the top
-        lo = (lo >> 16) | (hi << 48);
-        hi = (hi >> 16) | ((unsigned long long)(idx ^ (unsigned)N) << 48);
-        fill++; cnt++;
-      }
-    }
-    if (fill >= 4) {                                                 // the four oldest entries start 16*fill bits from the top
-      const int sh = 16 * fill - 64;                                 // 0, 16, 32 or 48
-      emit(sh ? (hi << sh) | (lo >> (64 - sh)) : hi);
-      fill -= 4;
-    }
-  }
-  if (fill) emit(hi >> (64 - 16 * fill));
-  cx.nnb[i] = (uint16_t)min(oq, d.maxq);
-  tot = (double)cnt;
-  const double invL = 1.0 / cx.L;
-  cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
-}
-
-// INNER list (radius rl = rc + skin) = the outer candidates currently within rl. The owner of row i walks the set bits
-// of its outer row (flattened walk: every lane advances through ITS candidates, so a warp iterates max(candidates)
-// times), tests the float32 nearest-image distance and stores the index of the copy to use -- the atom itself, or its
-// ghost shifted along the axes where the pair wraps (|d| > 1/2 of the box) -- straight into the [quad][atom] layout.
-// No image codes, no groups: the only padding is the last quad. Atoms are re-wrapped here, and the ghost table is
-// rebuilt: atom j gets a copy for every non-empty subset of the faces it is within rl (1 + 1e-3) of.
-// Boxes below 2 rl (or more ghosts than the shared array holds, or FP32 mode) use plain indices and the per-pair
-// minimum image (cx.mic).
-__device__ void build_inner_small(const Dev& d, Ctx& cx) {
-  const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
-  const int W = (N + 31) / 32;
-  __syncthreads();
-  wrap_and_refresh(cx, true);
-  __syncthreads();
+  // ---- ghost table (independent of the tiles)
   const bool own = tid < N;
   const float rg = (float)(rl * invL * (1.0 + 1e-3));
   float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -551,20 +539,20 @@ __device__ void build_inner_small(const Dev& d, Ctx& cx) {
     nb |= ((hb & 2u) ? pi.y < rg : pi.y > 1.f - rg) ? 2u : 0u;
     nb |= ((hb & 4u) ? pi.z < rg : pi.z > 1.f - rg) ? 4u : 0u;
   }
-  // exclusive block scan of the ghost counts
-  const int cnt = own ? (1 << __popc(nb)) - 1 : 0;
+  const int cnt = own ? (1 << __popc(nb)) - 1 : 0;      // exclusive block scan of the ghost counts
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
   if (lane == 31) cx.iscan[wid] = incl;
-  __syncthreads();
+  __syncthreads();                                       // also: bit matrix complete
+  if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t_tiles0);
   if (wid == 0) {
     const int v = lane < nw ? cx.iscan[lane] : 0;
-    int w = v;
+    int wsum = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-    cx.iscan[lane] = w - v;                               // exclusive prefix of the warp totals
-    if (lane == 31) cx.iscan[32] = w;                     // number of ghosts
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, wsum, o); if (lane >= o) wsum += t; }
+    cx.iscan[lane] = wsum - v;                            // exclusive prefix of the warp totals
+    if (lane == 31) cx.iscan[32] = wsum;                  // number of ghosts
   }
   __syncthreads();
   const int base = cx.iscan[wid] + incl - cnt, nghost = cx.iscan[32];
@@ -575,17 +563,27 @@ __device__ void build_inner_small(const Dev& d, Ctx& cx) {
     const uint32_t gi = ghost ? ((uint32_t)base << 8) | (hb << 3) | nb : 0u;
     cx.ginfo[tid] = gi;
     cx.ginfo_g[(size_t)cx.lbuf * Npad + tid] = gi;
-    if (ghost) write_ghosts(cx, tid, cx.sp[3 * tid], cx.sp[3 * tid + 1], cx.sp[3 * tid + 2]);
+    if (ghost) {
+      // index of the copy of this atom for every image subset g (0: the atom itself; subsets outside nb are never asked for)
+      uint32_t e[4];
+#pragma unroll
+      for (unsigned g = 0; g < 8; g++) {
+        const unsigned v = g == 0u ? (unsigned)tid : (unsigned)Npad + (unsigned)base + (unsigned)cx.gtbl[(nb << 3) + g] - 1u;
+        if (g & 1u) e[g >> 1] |= v << 16; else e[g >> 1] = v & 0xffffu;
+      }
+      *reinterpret_cast<uint4*>(cx.gidx + 8 * tid) = make_uint4(e[0], e[1], e[2], e[3]);
+      write_ghosts(cx, tid, cx.sp[3 * tid], cx.sp[3 * tid + 1], cx.sp[3 * tid + 2]);
+    }
   }
   __syncthreads();
-  const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
+  // ---- (2) rows
   int over = 0; double tot = 0.0;
-  if (own) { if (ghost) walk_outer_row<true>(d, cx, tid, pi, rl2f, over, tot); else walk_outer_row<false>(d, cx, tid, pi, rl2f, over, tot); }
+  if (own) { if (ghost) walk_hit_row<true>(d, cx, tid, pi, over, tot); else walk_hit_row<false>(d, cx, tid, pi, over, tot); }
   double r[2] = { tot, (double)over };
   bsum<2>(r, cx);
   cx.list_pairs = 0.5 * r[0];
   if (r[1] > 0.0) cx.status |= ST_NEIGH;
-  cx.L0 = L;
+  cx.L0 = L; cx.L0o = L;
   update_thr(d, cx);
 }
 
@@ -743,19 +741,19 @@ __device__ void build_inner(const Dev& d, Ctx& cx) {
 __device__ void build_list(const Dev& d, Ctx& cx) {
   const long long t_build0 = clock64();
   if (cx.in_move && cx.lbuf == cx.sv_lbuf) { cx.lbuf ^= 1; select_list(cx); }   // keep the list of the saved positions
+  if (d.small) {
+    build_small(d, cx);
+    if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; const unsigned long long dt = (unsigned long long)(clock64() - t_build0); cx.ct[NM_CT_CLK_BUILD] += dt; cx.ct[NM_CT_CLK_INNER] += dt; }
+    return;
+  }
   int flag = cx.thro2 < 0.0;
   if (!flag) {
     const double invL = 1.0 / cx.L;
     for (int i = threadIdx.x; i < cx.N; i += blockDim.x)
       flag |= disp2o(cx, i, cx.sp[3 * i], cx.sp[3 * i + 1], cx.sp[3 * i + 2], invL) > cx.thro2;
   }
-  if (__syncthreads_or(flag)) {
-    const long long t0 = clock64();
-    if (d.small) build_outer_small(d, cx);                    // the bit matrix carries no images: it survives a rejected move
-    else { cx.outer_in_move = cx.in_move; build_outer(d, cx); }
-    if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t0);
-  }
-  { const long long t0 = clock64(); if (d.small) build_inner_small(d, cx); else build_inner(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_INNER] += (unsigned long long)(clock64() - t0); }
+  if (__syncthreads_or(flag)) { const long long t0 = clock64(); cx.outer_in_move = cx.in_move; build_outer(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_OUTER] += (unsigned long long)(clock64() - t0); }
+  { const long long t0 = clock64(); build_inner(d, cx); if (threadIdx.x == 0) cx.ct[NM_CT_CLK_INNER] += (unsigned long long)(clock64() - t0); }
   if (threadIdx.x == 0) { cx.ct[NM_CT_LIST_BUILDS]++; cx.ct[NM_CT_CLK_BUILD] += (unsigned long long)(clock64() - t_build0); }
 }
 
@@ -860,11 +858,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
     // the allocation carries two spare rows, rows past nq are never used
     const char* lp = reinterpret_cast<const char*>(cx.list + i);
     const unsigned stride = (unsigned)Npad * 8u, sp_s = (unsigned)__cvta_generic_to_shared(cx.sp);
-    uint2 cur = *reinterpret_cast<const uint2*>(lp);
-    lp += stride;
-    for (int q = 0; q < nq; q++) {
-      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // for the next iteration
-      lp += stride;
+    auto do_quad = [&](const uint2 cur) {
       double xs = xi, ys = yi, zs = zi;
       if (IMG == 0) {
         const unsigned code = ((cur.x >> 13) & 7u) | ((cur.x >> 26) & 0x38u);
@@ -887,8 +881,30 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       lj_pair<EW, MIC, S32>(p[3], p[4], p[5], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       lj_pair<EW, MIC, S32>(p[6], p[7], p[8], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
       lj_pair<EW, MIC, S32>(p[9], p[10], p[11], xs, ys, zs, L_hi, L_lo, hL_hi, rc2_bits, fx, fy, fz, np, e, vir);
+    };
+#if NM_UNR == 2
+    // two quads per iteration: the same operations in the same order (the force sums stay sequential), twice the
+    // independent work in flight per warp -- for CTAs that have their SM to themselves
+    const uint2 dq = make_uint2((unsigned)N * 0x10001u, (unsigned)N * 0x10001u);
+    uint2 c0 = *reinterpret_cast<const uint2*>(lp), c1 = *reinterpret_cast<const uint2*>(lp + stride);
+    lp += 2 * stride;
+    for (int q = 0; q < nq; q += 2) {
+      const uint2 n0 = *reinterpret_cast<const uint2*>(lp), n1 = *reinterpret_cast<const uint2*>(lp + stride);
+      lp += 2 * stride;
+      if (q + 1 >= nq) c1 = dq;
+      do_quad(c0); do_quad(c1);
+      c0 = n0; c1 = n1;
+    }
+#else
+    uint2 cur = *reinterpret_cast<const uint2*>(lp);
+    lp += stride;
+    for (int q = 0; q < nq; q++) {
+      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // for the next iteration
+      lp += stride;
+      do_quad(cur);
       cur = nxt;
     }
+#endif
 #ifdef NM_DEBUG_CLOCKS   // per-atom loop clocks of thread 0 (tools/probe.py); compiled out of the product build
     if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_atom0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
 #endif
@@ -1404,7 +1420,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
 // ------------------------------------------------------------------ kernels
 // 'run 0' on the resident configurations: wrap, (re)build list, evaluate; optionally export.
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR, 1024 / NTHR)
+__global__ void __launch_bounds__(NTHR, NM_CTAS_PER_SM(NTHR))
 k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npairs_out) {
   constexpr bool S32 = NTHR == 1024;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1441,7 +1457,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
 
 // gen_sample (lammps_remcmc.py:665-691): MOD x move_mc (:643-658), then lammps_extract (:377-391)
 template <int NTHR>
-__global__ void __launch_bounds__(NTHR, 1024 / NTHR)
+__global__ void __launch_bounds__(NTHR, NM_CTAS_PER_SM(NTHR))
 k_cycle(Dev d, long long cycle) {
   constexpr bool S32 = NTHR == 1024;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1458,7 +1474,7 @@ k_cycle(Dev d, long long cycle) {
   __syncthreads();
   unsigned long long kclk[3] = { 0ull, 0ull, 0ull }; unsigned kcnt[3] = { 0u, 0u, 0u };   // per move kind (thread 0)
   for (int mv = 0; mv < d.mod; mv++) {
-    const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)(d.rep_offset + slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
+    const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)gslot(d, slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
     const double roll = rng_uniform(r, 0, P_ROLL);
     const long long t_mv0 = clock64();
     const int kind = roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2);
@@ -1549,7 +1565,7 @@ __global__ void k_schedule(Dev d, int nsm, int per_sm, long long cycle) {
       unsigned n[3] = { 0u, 0u, 0u };
       const int slot = d.cfg_slot[c];
       for (int mv = 0; mv < d.mod; mv++) {
-        const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)(d.rep_offset + slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
+        const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)gslot(d, slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
         const double roll = rng_uniform(r, 0, P_ROLL);
         n[roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2)]++;
       }
@@ -1607,28 +1623,34 @@ __global__ void k_exchange_pack(Dev d, double* dst) {
   dst[2 * k + 1] = pow(d.box[c], 3.0);
 }
 
-// replica_exchange (lammps_remcmc.py:776-803): one thread replays the sequential sweep of one pressure row.
-// table: [ns][2] by slot (copied to scratch e/v so swaps are seen by later pairs), perm[k] = source slot of slot k.
-__global__ void k_exchange_sweep(int np_, int nt, const double* table, const double* et, const double* pf,
-                                 const double* uniforms, uint32_t seed_lo, uint32_t seed_hi, long long cycle,
+// replica_exchange (lammps_remcmc.py:776-803): one thread replays the sequential sweep of one LOCAL pressure row (exchanges never
+// cross rows, :782-789, so a rank needs nothing from the other ranks to decide its swaps). table: (pe + ke, vol) per slot,
+// either the local pack (global_table = 0, local slot order) or the all-gathered job-wide table (global slot order); et / pf
+// come from the labels uploaded by nm_set_labels. The uniform of a pair is addressed by its GLOBAL draw index (row u, pair
+// n of the row: u * NT (NT-1) / 2 + n), so the decisions do not depend on the row -> rank map. perm[k] = local source slot
+// of local slot k.
+__global__ void k_exchange_sweep(Dev d, const double* table, int global_table, const double* uniforms, long long cycle,
                                  double* scratch, int* perm, unsigned long long* swaps) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= np_) return;
-  const int ns = np_ * nt;
-  double* e = scratch; double* vv = scratch + ns;
-  for (int t = 0; t < nt; t++) { const int k = u * nt + t; e[k] = table[2 * k]; vv[k] = table[2 * k + 1]; perm[k] = k; }
+  const int lr = blockIdx.x * blockDim.x + threadIdx.x, nt = d.nt;
+  if (lr >= d.nrep / nt) return;
+  const int u = d.row0 + lr * d.row_stride;
+  double* e = scratch; double* vv = scratch + d.nrep;
+  for (int t = 0; t < nt; t++) {
+    const int k = lr * nt + t, ks = global_table ? u * nt + t : k;
+    e[k] = table[2 * ks]; vv[k] = table[2 * ks + 1]; perm[k] = k;
+  }
   unsigned long long draw = (unsigned long long)u * (unsigned long long)(nt * (nt - 1) / 2), sw = 0;
   for (int v = nt - 1; v >= 0; v--)
     for (int w = 0; w < v; w++) {
-      const int i = u * nt + v, j = u * nt + w;
+      const int i = lr * nt + v, j = lr * nt + w;
       const double de = e[i] - e[j], dvol = vv[i] - vv[j];
-      const double dh = de * (1. / et[i] - 1. / et[j]) + (pf[i] - pf[j]) * dvol;
+      const double dh = de * (1. / d.label[4 * i] - 1. / d.label[4 * j]) + (d.label[4 * i + 1] - d.label[4 * j + 1]) * dvol;
       const double m = exp(dh), crit = isnan(m) ? m : (m < 1.0 ? m : 1.0);
       double un;
       if (uniforms) un = uniforms[draw];
       else {
         uint32_t wd[4];
-        philox4x32_10(seed_lo, seed_hi ^ NM_EXCH_KEY, (uint32_t)draw, P_EXCH, (uint32_t)cycle, (uint32_t)((unsigned long long)cycle >> 32), wd);
+        philox4x32_10(d.seed_lo, d.seed_hi ^ NM_EXCH_KEY, (uint32_t)draw, P_EXCH, (uint32_t)cycle, (uint32_t)((unsigned long long)cycle >> 32), wd);
         un = u53(wd[0], wd[1]);
       }
       draw++;
@@ -1641,9 +1663,9 @@ __global__ void k_exchange_sweep(int np_, int nt, const double* table, const dou
   atomicAdd(swaps, sw);
 }
 // apply the (row-local) permutation to the local slot -> configuration labels
-__global__ void k_exchange_permute(Dev d, const int* perm_global, int* tmp) {
+__global__ void k_exchange_permute(Dev d, const int* perm, int* tmp) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < d.nrep) tmp[k] = d.slot_cfg[perm_global[d.rep_offset + k] - d.rep_offset];
+  if (k < d.nrep) tmp[k] = d.slot_cfg[perm[k]];
 }
 __global__ void k_exchange_commit(Dev d, const int* tmp) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1709,7 +1731,8 @@ struct nm_engine {
   int threads; size_t smem; int nsm;
   std::vector<void*> allocs;
   double *stage_a, *stage_b, *stage_s;     // device staging: x/v AoS [nrep][3N], scalars [nrep][8]
-  double *ex_table, *ex_et, *ex_pf, *ex_uni, *ex_scratch; int *ex_perm, *ex_tmp; unsigned long long* ex_swaps;
+  double *ex_table, *ex_uni, *ex_scratch; int *ex_perm, *ex_tmp; unsigned long long* ex_swaps;
+  double* h_thermo; int* h_status;        // pinned host staging of nm_get_thermo (one synchronisation per cycle)
   long long* np_out;
   bool have_state, have_labels, have_thermo;
   int64_t launches;
@@ -1741,8 +1764,10 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   if (!cfg || !out) return fail(NM_EINVAL, "nm_create: null argument");
   if (cfg->struct_size != (int32_t)sizeof(nm_config)) return fail(NM_EINVAL, "nm_create: nm_config size mismatch (%d vs %zu)", cfg->struct_size, sizeof(nm_config));
   if (cfg->natoms < 2 || cfg->natoms > 8000) return fail(NM_EINVAL, "nm_create: natoms %d out of range [2, 8000] (13-bit neighbour indices; shared memory holds ~5000 atoms)", cfg->natoms);
-  if (cfg->n_rep < 1 || cfg->nt < 1 || cfg->n_rep % cfg->nt || cfg->rep_offset % cfg->nt || cfg->n_rep_global < cfg->rep_offset + cfg->n_rep)
-    return fail(NM_EINVAL, "nm_create: local slots must be whole pressure rows (n_rep=%d rep_offset=%d nt=%d global=%d)", cfg->n_rep, cfg->rep_offset, cfg->nt, cfg->n_rep_global);
+  const int row_stride = cfg->row_stride > 0 ? cfg->row_stride : 1;
+  if (cfg->n_rep < 1 || cfg->nt < 1 || cfg->n_rep % cfg->nt || cfg->rep_offset < 0 || cfg->rep_offset % cfg->nt || cfg->n_rep_global % cfg->nt ||
+      (cfg->rep_offset / cfg->nt + (cfg->n_rep / cfg->nt - 1) * row_stride + 1) * cfg->nt > cfg->n_rep_global)
+    return fail(NM_EINVAL, "nm_create: local slots must be whole pressure rows of the global grid (n_rep=%d rep_offset=%d row_stride=%d nt=%d global=%d)", cfg->n_rep, cfg->rep_offset, row_stride, cfg->nt, cfg->n_rep_global);
   if (cfg->precision != 64 && cfg->precision != 32 && cfg->precision != 0) return fail(NM_EINVAL, "nm_create: precision must be 64 or 32 (got %d)", cfg->precision);
   if (cfg->nstps < 1 || cfg->mod < 0 || cfg->ppos < 0 || cfg->pvol < 0 || cfg->ppos + cfg->pvol > 1.0 + 1e-12) return fail(NM_EINVAL, "nm_create: bad move parameters");
   if (!(cfg->rc > 0) || !(cfg->mass > 0)) return fail(NM_EINVAL, "nm_create: rc and mass must be positive");
@@ -1759,15 +1784,14 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   Dev& d = h->d;
   memset(&d, 0, sizeof d);
   const int N = cfg->natoms, nrep = cfg->n_rep;
-  d.N = N; d.Npad = ((N + 1) + 31) & ~31; d.nrep = nrep; d.nrep_global = cfg->n_rep_global; d.rep_offset = cfg->rep_offset; d.nt = cfg->nt;
+  d.N = N; d.Npad = ((N + 1) + 31) & ~31; d.nrep = nrep; d.nrep_global = cfg->n_rep_global; d.rep_offset = cfg->rep_offset; d.nt = cfg->nt; d.row0 = cfg->rep_offset / cfg->nt; d.row_stride = row_stride;
   d.nstps = cfg->nstps; d.mod = cfg->mod; d.bulk = cfg->bulk_move; d.text_rounding = cfg->text_rounding;
   d.ppos = cfg->ppos; d.pvol = cfg->pvol; d.lat = cfg->lat_scale; d.mass = cfg->mass; d.rc = cfg->rc;
   // default skin: tuned at the stationary state of the default workload (step sizes adapted to 50 % acceptance, 1.6
   // rebuilds per move): 0.4 where a rebuild costs 3 evaluations (hit-matrix builds), 0.3 with the cheaper two-level lists
   d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : 0.3);
-  // outer skin. LARGE: stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6. SMALL: the outer list is a
-  // bit matrix, its radius only sets how many candidates an inner build walks and how often the tile pass runs
-  d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : (N <= NSMALL ? 0.6 : 1.3);
+  // outer skin (LARGE mode only): stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6
+  d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 1.3;
   d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);
   {
     // list capacities: neighbours inside the list radius at the densest state we expect (rho* 1.6) plus slack,
@@ -1792,7 +1816,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
   const size_t per = (size_t)nrep * 3 * d.Npad;
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, 2 * per);
-  DA(d.list, ((size_t)nrep * 2 * (d.maxq + 1) + 2) * d.Npad); DA(d.lcur, nrep);
+  DA(d.list, (size_t)nrep * 2 * (d.maxq + LIST_SPARE_ROWS) * d.Npad); DA(d.lcur, nrep);
   if (d.small) { DA(d.hbT, (size_t)nrep * (d.Npad / 32) * d.Npad); DA(d.ginfo, (size_t)nrep * 2 * d.Npad); }       // one spare row per buffer: the loop prefetches one quad ahead
   DA(d.ltmp, (size_t)nrep * ((d.maxnbo + 3) & ~3) * d.Npad); DA(d.nnb, (size_t)nrep * 2 * d.Npad); DA(d.micmode, nrep);
   DA(d.olist, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.ocode, ((size_t)nrep * d.maxqo + 2) * d.Npad); DA(d.onq, (size_t)nrep * d.Npad);
@@ -1803,8 +1827,10 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
-  DA(h->ex_table, 2 * (size_t)nsg); DA(h->ex_et, nsg); DA(h->ex_pf, nsg); DA(h->ex_uni, (size_t)nsg * cfg->nt); DA(h->ex_scratch, 2 * (size_t)nsg);
-  DA(h->ex_perm, nsg); DA(h->ex_tmp, nrep); DA(h->ex_swaps, 1); DA(h->np_out, nrep);
+  DA(h->ex_table, 2 * (size_t)nrep); DA(h->ex_uni, (size_t)nsg * cfg->nt); DA(h->ex_scratch, 2 * (size_t)nrep);
+  DA(h->ex_perm, nrep); DA(h->ex_tmp, nrep); DA(h->ex_swaps, 1); DA(h->np_out, nrep);
+  if (cudaHostAlloc((void**)&h->h_thermo, sizeof(double) * (size_t)nrep * NM_THERMO_WIDTH, cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc((void**)&h->h_status, sizeof(int) * (size_t)nrep, cudaHostAllocDefault) != cudaSuccess) { nm_destroy(h); return fail(NM_ENOMEM, "nm_create: pinned host staging allocation failed"); }
   {
     std::vector<int> id(nrep); for (int k = 0; k < nrep; k++) id[k] = k;
     std::vector<double> neg(nrep, -1.0);
@@ -1828,6 +1854,8 @@ int nm_destroy(nm_engine* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->h_thermo) cudaFreeHost(h->h_thermo);
+  if (h->h_status) cudaFreeHost(h->h_status);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return NM_OK;
@@ -1848,8 +1876,8 @@ int nm_synchronize(nm_engine* h) {
 }
 
 static int check_status(nm_engine* h) {
-  std::vector<int> st(h->d.nrep);
-  CK(cudaMemcpyAsync(st.data(), h->d.status, sizeof(int) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
+  int* st = h->h_status;
+  CK(cudaMemcpyAsync(st, h->d.status, sizeof(int) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int c = 0; c < h->d.nrep; c++) {
     if (st[c] & ST_BOX) return fail(NM_EBOX, "configuration %d: box side below 2*rc (minimum image invalid)", c);
@@ -1956,8 +1984,12 @@ int nm_get_thermo(nm_engine* h, double* out) {
   if (!h || !out) return fail(NM_EINVAL, "nm_get_thermo: null argument");
   if (!h->have_thermo) return fail(NM_ESTATE, "nm_get_thermo: no cycle has run");
   CK(cudaSetDevice(h->cfg.device));
-  CK(cudaMemcpyAsync(out, h->d.thermo, sizeof(double) * (size_t)h->d.nrep * NM_THERMO_WIDTH, cudaMemcpyDeviceToHost, h->stream));
-  return check_status(h);
+  // thermo + status into pinned staging, one synchronisation, then a host copy into the caller's (pageable) array
+  const size_t nb = sizeof(double) * (size_t)h->d.nrep * NM_THERMO_WIDTH;
+  CK(cudaMemcpyAsync(h->h_thermo, h->d.thermo, nb, cudaMemcpyDeviceToHost, h->stream));
+  int r = check_status(h); if (r) return r;
+  memcpy(out, h->h_thermo, nb);
+  return NM_OK;
 }
 
 int nm_adapt(nm_engine* h) {
@@ -1980,25 +2012,22 @@ int nm_exchange_pack(nm_engine* h, void* dev_dst) {
   return NM_OK;
 }
 
-int nm_exchange_apply(nm_engine* h, const void* dev_table_global, const double* et_global, const double* pf_global,
-                      const double* uniforms, int64_t cycle, int32_t* perm_out, int64_t* swaps_out) {
-  if (!h || !dev_table_global || !et_global || !pf_global) return fail(NM_EINVAL, "nm_exchange_apply: null argument");
-  CK(cudaSetDevice(h->cfg.device));
-  const int ns = h->d.nrep_global, nt = h->d.nt, np_ = ns / nt;
-  CK(cudaMemcpyAsync(h->ex_et, et_global, sizeof(double) * ns, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->ex_pf, pf_global, sizeof(double) * ns, cudaMemcpyHostToDevice, h->stream));
-  const size_t nu = (size_t)np_ * nt * (nt - 1) / 2;
+// sweep of the local rows from `table` (local pack or job-wide table) + permutation of the local labels
+static int exchange_sweep(nm_engine* h, const double* dev_table, int global_table, const double* uniforms, int64_t cycle,
+                          int32_t* perm_out, int64_t* swaps_out) {
+  const int nt = h->d.nt, nrows = h->d.nrep / nt, npg = h->d.nrep_global / nt;
+  const size_t nu = (size_t)npg * nt * (nt - 1) / 2;
   if (uniforms && nu) CK(cudaMemcpyAsync(h->ex_uni, uniforms, sizeof(double) * nu, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->ex_swaps, 0, sizeof(unsigned long long), h->stream));
-  k_exchange_sweep<<<(np_ + 31) / 32, 32, 0, h->stream>>>(np_, nt, (const double*)dev_table_global, h->ex_et, h->ex_pf,
-      uniforms ? h->ex_uni : nullptr, h->d.seed_lo, h->d.seed_hi, (long long)cycle, h->ex_scratch, h->ex_perm, h->ex_swaps);
+  k_exchange_sweep<<<(nrows + 31) / 32, 32, 0, h->stream>>>(h->d, dev_table, global_table, uniforms ? h->ex_uni : nullptr, (long long)cycle,
+                                                            h->ex_scratch, h->ex_perm, h->ex_swaps);
   k_exchange_permute<<<(h->d.nrep + 127) / 128, 128, 0, h->stream>>>(h->d, h->ex_perm, h->ex_tmp);
   k_exchange_commit<<<(h->d.nrep + 127) / 128, 128, 0, h->stream>>>(h->d, h->ex_tmp);
   h->launches += 3;
   CK(cudaGetLastError());
   if (perm_out || swaps_out) {
     unsigned long long sw = 0;
-    if (perm_out) CK(cudaMemcpyAsync(perm_out, h->ex_perm, sizeof(int) * ns, cudaMemcpyDeviceToHost, h->stream));
+    if (perm_out) CK(cudaMemcpyAsync(perm_out, h->ex_perm, sizeof(int) * h->d.nrep, cudaMemcpyDeviceToHost, h->stream));
     if (swaps_out) CK(cudaMemcpyAsync(&sw, h->ex_swaps, sizeof sw, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (swaps_out) *swaps_out = (int64_t)sw;
@@ -2006,16 +2035,19 @@ int nm_exchange_apply(nm_engine* h, const void* dev_table_global, const double* 
   return NM_OK;
 }
 
+int nm_exchange_apply(nm_engine* h, const void* dev_table_global, const double* uniforms, int64_t cycle,
+                      int32_t* perm_out, int64_t* swaps_out) {
+  if (!h || !dev_table_global) return fail(NM_EINVAL, "nm_exchange_apply: null argument");
+  if (!h->have_labels) return fail(NM_ESTATE, "nm_exchange_apply: labels not set");
+  CK(cudaSetDevice(h->cfg.device));
+  return exchange_sweep(h, (const double*)dev_table_global, 1, uniforms, cycle, perm_out, swaps_out);
+}
+
 int nm_exchange(nm_engine* h, const double* uniforms, int64_t cycle, int32_t* perm_out, int64_t* swaps_out) {
   if (!h) return fail(NM_EINVAL, "null engine");
-  if (h->d.nrep != h->d.nrep_global) return fail(NM_EINVAL, "nm_exchange: single-rank call on a sharded engine; use pack + all-gather + apply");
   if (!h->have_labels) return fail(NM_ESTATE, "nm_exchange: labels not set");
   int r = nm_exchange_pack(h, h->ex_table); if (r) return r;
-  std::vector<double> lab(4 * (size_t)h->d.nrep), et(h->d.nrep), pf(h->d.nrep);
-  CK(cudaMemcpyAsync(lab.data(), h->d.label, sizeof(double) * lab.size(), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  for (int k = 0; k < h->d.nrep; k++) { et[k] = lab[4 * k]; pf[k] = lab[4 * k + 1]; }
-  return nm_exchange_apply(h, h->ex_table, et.data(), pf.data(), uniforms, cycle, perm_out, swaps_out);
+  return exchange_sweep(h, h->ex_table, 0, uniforms, cycle, perm_out, swaps_out);
 }
 
 int nm_get_counters(nm_engine* h, uint64_t* out) {

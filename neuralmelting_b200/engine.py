@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnm_b200.so")
+LIB_PATH = os.environ.get("NM_B200_LIB") or os.path.join(_HERE, "libnm_b200.so")      # NM_B200_LIB: development builds (tools/)
 
 THERMO_WIDTH = 18
 THERMO_COLS = ("temp", "pe", "ke", "virial", "box", "vol", "dx", "dv", "dt",
@@ -34,7 +34,7 @@ class NmConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("natoms", C.c_int32),
                 ("n_rep", C.c_int32), ("n_rep_global", C.c_int32), ("rep_offset", C.c_int32),
                 ("nt", C.c_int32), ("precision", C.c_int32), ("nstps", C.c_int32), ("mod", C.c_int32),
-                ("bulk_move", C.c_int32), ("text_rounding", C.c_int32),
+                ("bulk_move", C.c_int32), ("text_rounding", C.c_int32), ("row_stride", C.c_int32), ("reserved0", C.c_int32),
                 ("ppos", C.c_double), ("pvol", C.c_double), ("lat_scale", C.c_double),
                 ("mass", C.c_double), ("rc", C.c_double), ("skin", C.c_double), ("skin_outer", C.c_double),
                 ("seed", C.c_uint64), ("stream", C.c_void_p)]
@@ -71,7 +71,7 @@ def load_library():
     L.nm_run_cycle.argtypes = [C.c_void_p, C.c_int64]
     L.nm_get_thermo.argtypes = [C.c_void_p, C.c_void_p]
     L.nm_exchange_pack.argtypes = [C.c_void_p, C.c_void_p]
-    L.nm_exchange_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.nm_exchange_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.nm_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.nm_get_counters.argtypes = [C.c_void_p, C.c_void_p]
     L.nm_rdf_counts.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
@@ -113,19 +113,20 @@ def device_count():
 class Engine:
     """All local replicas of the (P, T) grid on one GPU.
 
-    Host arrays are in local slot order k = i*NT + j - rep_offset (lammps_remcmc.py:117).
+    Host arrays are in local slot order (lammps_remcmc.py:117: k = i*NT + j): local pressure row lr is global row
+    rep_offset/NT + lr*row_stride (row_stride 1: contiguous block; G ranks cyclic: rep_offset = rank*NT, row_stride = G).
     """
 
-    def __init__(self, natoms, n_rep, nt, n_rep_global=None, rep_offset=0, device=0, nstps=8, mod=128,
+    def __init__(self, natoms, n_rep, nt, n_rep_global=None, rep_offset=0, row_stride=1, device=0, nstps=8, mod=128,
                  bulk_move=False, ppos=0.125, pvol=0.125, lat_scale=1.122, mass=1.0, rc=2.5, skin=0.0, skin_outer=0.0,
                  seed=256, text_rounding=True, precision=64, stream=None):
         L = load_library()
         self.natoms, self.n_rep, self.nt = int(natoms), int(n_rep), int(nt)
         self.n_rep_global = int(n_rep_global if n_rep_global is not None else n_rep)
-        self.rep_offset = int(rep_offset)
+        self.rep_offset, self.row_stride = int(rep_offset), max(1, int(row_stride))
         self.mod, self.nstps = int(mod), int(nstps)
         cfg = NmConfig(C.sizeof(NmConfig), device, natoms, n_rep, self.n_rep_global, rep_offset, nt, precision,
-                       nstps, mod, int(bool(bulk_move)), int(bool(text_rounding)), ppos, pvol, lat_scale, mass, rc,
+                       nstps, mod, int(bool(bulk_move)), int(bool(text_rounding)), self.row_stride, 0, ppos, pvol, lat_scale, mass, rc,
                        skin, skin_outer, seed, None)
         self._h = C.c_void_p()
         _check(L.nm_create(C.byref(cfg), C.byref(self._h)))
@@ -210,22 +211,28 @@ class Engine:
     def exchange_pack(self, dev_ptr):
         _check(self._L.nm_exchange_pack(self._h, C.c_void_p(dev_ptr)))
 
-    def exchange_apply(self, dev_table_ptr, et_global, pf_global, cycle, uniforms=None, want_perm=True):
-        et_global, pf_global = _f64(et_global, (self.n_rep_global,)), _f64(pf_global, (self.n_rep_global,))
-        uniforms = _f64(uniforms)
-        perm = np.empty(self.n_rep_global, dtype=np.int32) if want_perm else None
-        swaps = C.c_int64(0)
-        _check(self._L.nm_exchange_apply(self._h, C.c_void_p(dev_table_ptr), _ptr(et_global), _ptr(pf_global),
-                                         _ptr(uniforms), int(cycle), _ptr(perm),
-                                         C.addressof(swaps) if want_perm else None))
-        return perm, swaps.value
+    def global_slots(self):
+        """global slot index k = i*NT + j of every local slot"""
+        lr, j = np.divmod(np.arange(self.n_rep), self.nt)
+        return (self.rep_offset // self.nt + lr * self.row_stride) * self.nt + j
 
-    def exchange(self, cycle, uniforms=None):
+    def exchange(self, cycle, uniforms=None, want_perm=True):
+        """replica exchange of the local pressure rows (rows never exchange with each other, lammps_remcmc.py:782-789).
+        uniforms: optional job-wide array in global draw order. want_perm=False: asynchronous, returns (None, None)."""
         uniforms = _f64(uniforms)
-        perm = np.empty(self.n_rep_global, dtype=np.int32)
+        perm = np.empty(self.n_rep, dtype=np.int32) if want_perm else None
         swaps = C.c_int64(0)
-        _check(self._L.nm_exchange(self._h, _ptr(uniforms), int(cycle), _ptr(perm), C.addressof(swaps)))
-        return perm, swaps.value
+        _check(self._L.nm_exchange(self._h, _ptr(uniforms), int(cycle), _ptr(perm), C.addressof(swaps) if want_perm else None))
+        return (perm, swaps.value) if want_perm else (None, None)
+
+    def exchange_apply(self, dev_table_ptr, cycle, uniforms=None, want_perm=True):
+        """the same sweep reading a job-wide device table double[n_rep_global][2] (global slot order)"""
+        uniforms = _f64(uniforms)
+        perm = np.empty(self.n_rep, dtype=np.int32) if want_perm else None
+        swaps = C.c_int64(0)
+        _check(self._L.nm_exchange_apply(self._h, C.c_void_p(dev_table_ptr), _ptr(uniforms), int(cycle), _ptr(perm),
+                                         C.addressof(swaps) if want_perm else None))
+        return (perm, swaps.value) if want_perm else (None, None)
 
     # -- bookkeeping
     def counters(self):
