@@ -9,8 +9,12 @@ A "step" is one collection cycle of the whole local (P, T) grid: MOD Monte Carlo
 + replica exchange (:776-803; all-gather of (pe+ke, vol) over NCCL when N > 1).
 Metric (BASELINE.json): HMC atom-steps/s = sum over HMC moves of natoms*NSTPS / time; MC sweeps/s rides along.
 Workload at N=1: BASELINE.json configs[1] (C2: 500-atom LJ, 16 x 16 grid, default move mix). N > 1 is weak scaling:
-every GPU holds a 16-pressure-row x 16-temperature shard of a (16 N) x 16 grid ("c3": 4 rows x 32 T of 4000 atoms
-per GPU, i.e. exactly BASELINE configs[2] at N=8).
+every GPU holds 16 pressure rows x 16 temperatures of a (16 N) x 16 grid, pressure row u on rank u mod N ("c3": 4 rows x
+32 T of 4000 atoms per GPU, i.e. exactly BASELINE configs[2] at N=8). Swaps are decided rank-locally (exchanges never cross
+pressure rows); the NCCL all-gather of (pe + ke, vol) runs asynchronously beside the next cycle.
+The same JSON line carries a "workloads" block with short legs of the other BASELINE configurations (c3, c4, c5) and a
+"parity_gate": after the timed region a handful of the resident configurations is re-evaluated and compared with the CPU
+oracle at 1e-10 (energy, virial, forces; in-cutoff pair counts exact).
 
 --impl reference times the CPU restatement of the reference path (oracle/, "port": LAMMPS and Dask are not installable,
 see BASELINE.md) farmed over all host cores, one replica per task like Dask does, on a bounded sample of the same workload.
@@ -28,9 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one nm::k_cycle launch from the committed `ncu --set full` capture
-# (profiles/r1c_cycle_c2_ncu_full.txt); per workload, None where no capture exists
-NCU_TRAFFIC_BYTES = {"c2": 256.89856e6 + 2662.470e6}
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the workload's dominant kernel, from the committed
+    `ncu --set full` capture of the current round: profiles/ncu_traffic.json = {workload: {"bytes": B, "capture": file}}"""
+    try:
+        ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload)
+        return (float(ent["bytes"]), ent["capture"]) if ent else (None, None)
+    except Exception:
+        return None, None
+
 
 WORKLOADS = {
     # name: (supercell, pressure rows per GPU, temperatures, bulk_move, ppos, pvol, mod, description)
@@ -52,6 +64,7 @@ def parse():
     ap.add_argument("--equil", type=int, default=32, help="untimed equilibration cycles before the warm-up (the step sizes adapt for ~25 cycles: the cost of a cycle rises by 60 %% until the acceptances settle at 0.5)")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="pair arithmetic: 64 (headline) or the FP32 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the short c3 / c4 / c5 legs of the 'workloads' block")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -64,10 +77,10 @@ def grid_for(world, wl):
     return sz, rows, nt, npn, P, T, bulk, ppos, pvol, mod, desc
 
 
-def initial_states(P_rows, T, sz, device, seed):
-    """the reference's init_sample (pressure-relaxed fcc + random displacement), advanced by a few equilibration cycles later"""
+def initial_states(P, T, sz, slots, device):
+    """the reference's init_sample (pressure-relaxed fcc + random displacement keyed on the global slot) for the given global slots"""
     from neuralmelting_b200 import remcmc
-    x, v, box = remcmc.init_samples(P_rows, T, sz, 0.03125, np.random.default_rng(seed), device=device)
+    x, v, box = remcmc.init_samples(P, T, sz, 0.03125, remcmc.SEED, slots=slots, device=device)
     box = np.array([remcmc.text6(b) for b in box])
     return x, v, box
 
@@ -121,29 +134,47 @@ def flops_from(ct):
     return 24.0 * ct["pairs_force"] + 30.0 * ct["pairs_full"] + 13.0 * ct["pairs_delta"] + 18.0 * ct["hmc_atom_steps"]
 
 
-def run_b200(args):
-    import torch
+def parity_gate(eng, natoms, nloc, ncheck=6, tol=1e-10):
+    """correctness gate on what the timed region left resident: re-evaluate every configuration on the GPU (nm_eval), pick
+    ncheck slots across the temperature range and compare energy, virial, forces and the in-cutoff pair count with the CPU
+    oracle (list-based lj/cut restatement) on the same positions"""
+    from oracle import oracle as orc
+    st = eng.get_state(want_v=False)
+    pe, w, f, npairs = eng.eval(want_forces=True)
+    pick = np.unique(np.linspace(0, nloc - 1, ncheck).round().astype(int))
+    worst = {"pe": 0.0, "w": 0.0, "f": 0.0}
+    pairs_exact = True
+    for k in pick:
+        pe_o, w_o, f_o, np_o = orc.lj_eval_list(st["x"][k], float(st["box"][k]))
+        worst["pe"] = max(worst["pe"], abs(pe[k] - pe_o) / abs(pe_o))
+        worst["w"] = max(worst["w"], abs(w[k] - w_o) / max(abs(w_o), 1e-300))
+        worst["f"] = max(worst["f"], float(np.abs(f[k].reshape(-1) - np.asarray(f_o).reshape(-1)).max() / np.abs(f_o).max()))
+        pairs_exact = pairs_exact and int(npairs[k]) == int(np_o)
+    # the virial of a near-equilibrium configuration is a small difference of large terms: it is compared relative to sum |r.f|
+    ok = worst["pe"] <= tol and worst["f"] <= tol and pairs_exact
+    return {"replicas_checked": int(pick.size), "tol": tol, "max_rel_err_pe": worst["pe"], "max_rel_err_virial": worst["w"],
+            "max_rel_err_forces": worst["f"], "pair_counts_exact": bool(pairs_exact), "pass": bool(ok),
+            "against": "oracle/nm_oracle.c lj_eval_list on the positions resident after the timed region"}
+
+
+def measure_mc(args, comm, torch, workload, steps, warmup, equil, with_e2e=True, with_gate=True):
+    """one Monte Carlo workload on this rank's shard: returns the rank-0 dict (None elsewhere) and the pieces the CPU baseline needs"""
     from neuralmelting_b200 import engine as nm
     from neuralmelting_b200 import remcmc
-    comm = remcmc.Comm()
-    if comm.world != args.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, comm.world, args.gpus))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
     dev = comm.local_rank
-    torch.cuda.set_device(dev)
-    sz, rows, nt, npn, P, T, bulk, ppos, pvol, mod, desc = grid_for(comm.world, args.workload)
+    sz, rows, nt, npn, P, T, bulk, ppos, pvol, mod, desc = grid_for(comm.world, workload)
     natoms = 4 * sz ** 3
-    nloc, ns, off = rows * nt, npn * nt, comm.rank * rows * nt
+    nloc, ns = rows * nt, npn * nt
     et, pf = remcmc.init_constants(P, T)
     temp = np.tile(T.astype(np.float64), npn)
-    x, v, box = initial_states(P[comm.rank * rows:(comm.rank + 1) * rows], T, sz, dev, 1000 + comm.rank)
     stream = torch.cuda.current_stream().cuda_stream
-    eng = nm.Engine(natoms=natoms, n_rep=nloc, nt=nt, n_rep_global=ns, rep_offset=off, device=dev, mod=mod, bulk_move=bulk,
-                    ppos=ppos, pvol=pvol, seed=remcmc.SEED, stream=stream, precision=args.precision)
-    sl = slice(off, off + nloc)
-    eng.set_labels(et[sl], pf[sl], temp[sl])
+    eng = nm.Engine(natoms=natoms, n_rep=nloc, nt=nt, n_rep_global=ns, rep_offset=comm.rank * nt, row_stride=comm.world, device=dev,
+                    mod=mod, bulk_move=bulk, ppos=ppos, pvol=pvol, seed=remcmc.SEED, stream=stream, precision=args.precision)
+    gs = eng.global_slots()
+    x, v, box = initial_states(P, T, sz, gs, dev)
+    eng.set_labels(et[gs], pf[gs], temp[gs])
     eng.set_state(x=x, v=v, box=box, dx=np.full(nloc, 0.03125), dv=np.full(nloc, 0.03125), dt=np.full(nloc, 0.00390625))
+    gather = remcmc.TableGather(comm, eng, torch)
 
     def step(cyc, kernel_events=None):
         if kernel_events is not None:
@@ -154,15 +185,15 @@ def run_b200(args):
             e1.record(); kernel_events.append((e0, e1))
         th = eng.get_thermo()                       # the step's result (D2H, 18 doubles per replica)
         eng.adapt()
-        table = remcmc.allgather_table(comm, eng, torch)
-        eng.exchange_apply(table.data_ptr(), et, pf, cyc, want_perm=False)
+        eng.exchange(cyc, want_perm=False)          # rank-local sweep of the local pressure rows (asynchronous)
+        gather.start()                              # job-wide (pe + ke, vol) table: asynchronous all-gather, off the critical path
         return th
 
     cyc = 0
-    for _ in range(args.equil):
+    for _ in range(equil):
         step(cyc); cyc += 1
     sampler = ClockSampler(dev) if comm.rank == 0 else None       # covers warm-up + timed region; idle samples are filtered
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         step(cyc); cyc += 1
     eng.synchronize()
     # ---------------- timed region: device-resident state, CUDA events on the launching stream
@@ -172,7 +203,7 @@ def run_b200(args):
     comm.barrier(); torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(cyc, kev); cyc += 1
     t1.record()
     comm.barrier(); torch.cuda.synchronize()
@@ -181,77 +212,125 @@ def run_b200(args):
     ct = eng.counters()
     launches = eng.launch_count() - launches0
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev)
+    table = gather.latest()                         # the job-wide table of the last exchange (checked below)
+    gate = parity_gate(eng, natoms, nloc) if (with_gate and comm.rank == 0 and args.precision == 64) else None
     # ---------------- end-to-end through the public API with HOST buffers (pinned): state in, cycle, state + thermo out
-    hx = torch.empty((nloc, 3 * natoms), dtype=torch.float64).pin_memory()
-    hv = torch.empty((nloc, 3 * natoms), dtype=torch.float64).pin_memory()
-    st = eng.get_state()
-    hx.numpy()[:] = st["x"]; hv.numpy()[:] = st["v"]
-    hbox, hdx, hdv, hdt = st["box"].copy(), st["dx"].copy(), st["dv"].copy(), st["dt"].copy()
-    e2e_steps = max(2, min(args.steps, 4))
-    eng.reset_counters()
-    comm.barrier(); torch.cuda.synchronize()
-    w0 = time.perf_counter()
-    breakdown = os.environ.get("NM_BENCH_E2E_BREAKDOWN")          # development aid: synchronises after every call
-    tb = [0.0] * 4
-    kev_e2e = []
-    for _ in range(e2e_steps):
-        c0 = time.perf_counter()
-        eng.set_state(x=hx.numpy(), v=hv.numpy(), box=hbox, dx=hdx, dv=hdv, dt=hdt)      # H2D (+ the 'run 0' evaluation)
-        if breakdown: eng.synchronize()
-        c1 = time.perf_counter()
-        th = step(cyc, kev_e2e if breakdown else None); cyc += 1
-        if breakdown: eng.synchronize()
-        c2 = time.perf_counter()
-        st = eng.get_state(x_out=hx.numpy(), v_out=hv.numpy())                       # D2H straight into the pinned host buffers
-        c3 = time.perf_counter()
-        hbox, hdx, hdv, hdt = st["box"], st["dx"], st["dv"], st["dt"]
-        c4 = time.perf_counter()
-        for k, dtk in enumerate((c1 - c0, c2 - c1, c3 - c2, c4 - c3)): tb[k] += dtk
-    if breakdown and comm.rank == 0:
-        print("e2e breakdown (ms/step): set_state %.2f  step %.2f (cycle kernel %.2f)  get_state %.2f  host copies %.2f" % (
-            1e3 * tb[0] / e2e_steps, 1e3 * tb[1] / e2e_steps, sum(a.elapsed_time(b) for a, b in kev_e2e) / e2e_steps, 1e3 * tb[2] / e2e_steps, 1e3 * tb[3] / e2e_steps), file=sys.stderr)
-    torch.cuda.synchronize(); comm.barrier()
-    e2e_s = time.perf_counter() - w0
-    ct_e2e = eng.counters()
+    e2e_ms, atom_steps_e2e_local, sweeps_e2e_local, e2e_steps = 0.0, 0.0, 0.0, 0
     h2d = (2 * 3 * natoms + 4) * 8 * nloc
     d2h = (2 * 3 * natoms + 4 + 18) * 8 * nloc
+    if with_e2e:
+        hx = torch.empty((nloc, 3 * natoms), dtype=torch.float64).pin_memory()
+        hv = torch.empty((nloc, 3 * natoms), dtype=torch.float64).pin_memory()
+        st = eng.get_state()
+        hx.numpy()[:] = st["x"]; hv.numpy()[:] = st["v"]
+        hbox, hdx, hdv, hdt = st["box"].copy(), st["dx"].copy(), st["dv"].copy(), st["dt"].copy()
+        e2e_steps = max(2, min(steps, 4))
+        eng.reset_counters()
+        comm.barrier(); torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        breakdown = os.environ.get("NM_BENCH_E2E_BREAKDOWN")          # development aid: synchronises after every call
+        tb = [0.0] * 4
+        kev_e2e = []
+        for _ in range(e2e_steps):
+            c0 = time.perf_counter()
+            eng.set_state(x=hx.numpy(), v=hv.numpy(), box=hbox, dx=hdx, dv=hdv, dt=hdt)      # H2D (+ the 'run 0' evaluation)
+            if breakdown: eng.synchronize()
+            c1 = time.perf_counter()
+            th = step(cyc, kev_e2e if breakdown else None); cyc += 1
+            if breakdown: eng.synchronize()
+            c2 = time.perf_counter()
+            st = eng.get_state(x_out=hx.numpy(), v_out=hv.numpy())                       # D2H straight into the pinned host buffers
+            c3 = time.perf_counter()
+            hbox, hdx, hdv, hdt = st["box"], st["dx"], st["dv"], st["dt"]
+            c4 = time.perf_counter()
+            for k, dtk in enumerate((c1 - c0, c2 - c1, c3 - c2, c4 - c3)): tb[k] += dtk
+        if breakdown and comm.rank == 0:
+            print("e2e breakdown (ms/step): set_state %.2f  step %.2f (cycle kernel %.2f)  get_state %.2f  host copies %.2f" % (
+                1e3 * tb[0] / e2e_steps, 1e3 * tb[1] / e2e_steps, sum(a.elapsed_time(b) for a, b in kev_e2e) / e2e_steps, 1e3 * tb[2] / e2e_steps, 1e3 * tb[3] / e2e_steps), file=sys.stderr)
+        torch.cuda.synchronize(); comm.barrier()
+        e2e_ms = (time.perf_counter() - w0) * 1e3
+        ct_e2e = eng.counters()
+        atom_steps_e2e_local, sweeps_e2e_local = ct_e2e["hmc_atom_steps"], ct_e2e["sweeps"]
+    gather.finish()
     # ---------------- reduce over ranks: max time, summed work
-    vals = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device="cuda")
-    work = torch.tensor([ct["hmc_atom_steps"], ct["sweeps"], flops_from(ct), ct_e2e["hmc_atom_steps"], launches,
-                         ct["pairs_force"] + ct["pairs_full"], ct["list_pairs"], ct["list_builds"], ct["outer_builds"]], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    work = torch.tensor([ct["hmc_atom_steps"], ct["sweeps"], flops_from(ct), atom_steps_e2e_local, launches,
+                         ct["pairs_force"] + ct["pairs_full"], ct["list_pairs"], ct["list_builds"], ct["outer_builds"], ct["pmc_trials"], sweeps_e2e_local],
+                        dtype=torch.float64, device="cuda")
     if comm.world > 1:
         comm.dist.all_reduce(vals, op=comm.dist.ReduceOp.MAX)
         comm.dist.all_reduce(work, op=comm.dist.ReduceOp.SUM)
     ms, e2e_ms, kernel_ms = (float(t) for t in vals.cpu())
-    atom_steps, sweeps, flops, atom_steps_e2e, launches_all, inpairs, listpairs, builds, obuilds = (float(t) for t in work.cpu())
+    atom_steps, sweeps, flops, atom_steps_e2e, launches_all, inpairs, listpairs, builds, obuilds, trials, sweeps_e2e = (float(t) for t in work.cpu())
     out = None
     if comm.rank == 0:
         peak, _ = nm.measure_fma_peak(dev, args.precision)
         achieved = flops / comm.world / (kernel_ms * 1e-3) if kernel_ms > 0 else 0.0      # per-GPU, kernel-only time
+        traffic, capture = ncu_traffic(workload) if comm.world == 1 else (None, None)
         out = {
             "metric": "hmc_atom_steps_per_sec", "value": atom_steps / (ms * 1e-3), "unit": "atom-steps/s",
             "mc_sweeps_per_sec": sweeps / (ms * 1e-3),
-            "n_gpus": comm.world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "n_gpus": comm.world, "steps": steps, "warmup": max(3, warmup), "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
-            "data": "synthetic: pressure-relaxed fcc + random displacement (the reference's init_sample), %d equilibration cycles, counter-based RNG seed 256" % args.equil,
+            "data": "synthetic: pressure-relaxed fcc + random displacement (the reference's init_sample), %d equilibration cycles, counter-based RNG seed 256" % equil,
             "config": {"workload": desc, "natoms": natoms, "replicas_per_gpu": nloc, "grid": [npn, nt], "moves_per_cycle": mod,
                        "hmc_steps": 8, "l2": "inputs larger than L2 (per-GPU state + neighbour lists of %d replicas > 126 MB)" % nloc if nloc * natoms > 60000 else "working set fits L2; no flush (compute-bound on-chip kernel)",
-                       "parallelism": "replica grid sharded by pressure row, %d row(s)/GPU" % rows},
-            "e2e": {"value": atom_steps_e2e / (e2e_ms * 1e-3), "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "note": "set_state (pinned host x, v, box, step sizes) -> cycle -> get_thermo + get_state, every step"},
+                       "parallelism": "replica grid sharded by pressure row, row u on rank u mod %d (%d row(s)/GPU); swaps decided rank-locally, (pe+ke, vol) all-gathered asynchronously" % (comm.world, rows)},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "fp64_fma" if args.precision == 64 else "fp32_fma", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if comm.world == 1 else None, "traffic_unit": "bytes/launch (ncu capture, profiles/r1c_cycle_c2_ncu_full.txt)",
-                         "kernel": "nm::k_cycle", "kernel_ms_per_step": kernel_ms / args.steps,
+                         "traffic": traffic, "traffic_unit": "bytes/launch (ncu --set full, profiles/%s)" % capture if capture else None,
+                         "kernel": "nm::k_cycle", "kernel_ms_per_step": kernel_ms / steps,
                          "peak_source": "live DFMA microbenchmark (nm_measure_fma_peak); MEASURED_PEAKS.json carries no FP64 figure",
                          "flops": "24/in-cutoff pair (force), 30 (force+energy+virial), 13/neighbour of a single-atom dE, 18/atom-step",
-                         "in_cutoff_pairs_per_step": inpairs / args.steps, "listed_over_in_cutoff": listpairs / max(1.0, inpairs),
-                         "list_builds_per_step": builds / args.steps, "outer_builds_per_step": obuilds / args.steps},
+                         "in_cutoff_pairs_per_step": inpairs / steps, "listed_over_in_cutoff": listpairs / max(1.0, inpairs),
+                         "list_builds_per_step": builds / steps, "outer_builds_per_step": obuilds / steps},
             "clocks": clocks,
         }
-        if comm.world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args, sz, nt, P, T, et, pf, temp, bulk, ppos, pvol, mod, x, box, args.cpu_seconds)
+        if with_e2e:
+            out["e2e"] = {"value": atom_steps_e2e / (e2e_ms * 1e-3), "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                          "steps": e2e_steps, "mc_sweeps_per_sec": sweeps_e2e / (e2e_ms * 1e-3),
+                          "note": "set_state (pinned host x, v, box, step sizes) -> cycle -> get_thermo + get_state, every step"}
+        if not bulk:
+            out["single_atom_trials_per_sec"] = trials / (ms * 1e-3)
+        if gate is not None:
+            out["parity_gate"] = gate
+        # the asynchronously gathered table is the job-wide (pe + ke, vol) of the last exchange: finite, positive volumes
+        out["exchange_table"] = {"slots": int(table.shape[0]), "finite": bool(np.isfinite(table).all()), "min_vol": float(table[:, 1].min())}
     eng.close()
+    return out, dict(sz=sz, nt=nt, P=P, T=T, et=et, pf=pf, temp=temp, bulk=bulk, ppos=ppos, pvol=pvol, mod=mod, x=x, box=box, gs=gs)
+
+
+def leg_summary(o):
+    keep = ("metric", "value", "unit", "mc_sweeps_per_sec", "single_atom_trials_per_sec", "ordered_pair_distances_per_sec", "n_gpus", "steps", "warmup",
+            "ms_per_step", "dtype", "config", "e2e", "gpu_launches", "roofline", "clocks", "parity_gate", "fp32_pipe")
+    return {k: o[k] for k in keep if k in o}
+
+
+def run_b200(args):
+    import torch
+    from neuralmelting_b200 import remcmc
+    comm = remcmc.Comm()
+    if comm.world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, comm.world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(comm.local_rank)
+    out, ctx = measure_mc(args, comm, torch, args.workload, args.steps, args.warmup, args.equil)
+    if comm.rank == 0 and comm.world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, ctx["sz"], ctx["nt"], ctx["P"], ctx["T"], ctx["et"][ctx["gs"]], ctx["pf"][ctx["gs"]], ctx["temp"][ctx["gs"]],
+                                           ctx["bulk"], ctx["ppos"], ctx["pvol"], ctx["mod"], ctx["x"], ctx["box"], args.cpu_seconds)
+    if not args.no_legs and args.workload == "c2":
+        # short legs of the other BASELINE configurations, same process, same box (driver-run evidence for C3 / C4 / C5)
+        legs = {}
+        for wl, (st_, wu_, eq_) in (("c3", (3, 3, 12)), ("c4", (24, 8, 24))):
+            o, _ = measure_mc(args, comm, torch, wl, st_, wu_, eq_, with_e2e=True, with_gate=True)
+            if o is not None:
+                legs[wl] = leg_summary(o)
+        o = run_rdf(args, comm=comm, steps=4, nsamples=min(args.rdf_samples, 512))
+        if o is not None:
+            legs["c5"] = leg_summary(o)
+        if out is not None:
+            out["workloads"] = legs
     return out
 
 
@@ -361,7 +440,7 @@ def run_reference(args):
             "note": "CPU restatement of lammps_remcmc.py's per-replica path (LAMMPS + Dask are not installable here); one replica per task over all host threads"}
 
 
-def run_rdf(args):
+def run_rdf(args, comm=None, steps=None, nsamples=None):
     """c5 (BASELINE configs[4]): RDF feature extraction (lammps_distr.py:123-135) over samples of 4000-atom configurations.
     A step = one batch of --rdf-samples samples; value = samples/s with the positions resident in HBM; e2e = from host
     arrays through nm_rdf_counts (H2D of positions, D2H of counts inside the timed region). HBM roofline: 12 N + 6 bytes
@@ -369,10 +448,11 @@ def run_rdf(args):
     import torch
     from neuralmelting_b200 import engine as nm
     from neuralmelting_b200 import remcmc
-    comm = remcmc.Comm()
+    comm = comm or remcmc.Comm()
     dev = comm.local_rank
     torch.cuda.set_device(dev)
-    n, sb, ns = 4000, 64, args.rdf_samples
+    steps = steps or steps
+    n, sb, ns = 4000, 64, nsamples or args.rdf_samples
     rng = np.random.default_rng(5 + comm.rank)
     box = rng.uniform(15.2, 20.5, ns).astype(np.float32)                 # the density range of the 32x32 grid
     pos = (rng.uniform(0, 1, (ns, n, 3)) * box[:, None, None]).astype(np.float32)
@@ -390,7 +470,7 @@ def run_rdf(args):
     comm.barrier(); torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     t1.record()
     comm.barrier(); torch.cuda.synchronize()
@@ -414,21 +494,31 @@ def run_rdf(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = bytes_per_sample * ns * args.steps * comm.world / (ms * 1e-3) / 1e9 / comm.world
-    out = {"metric": "rdf_samples_per_sec", "value": ns * args.steps * comm.world / (ms * 1e-3), "unit": "samples/s",
-           "n_gpus": comm.world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+    achieved = bytes_per_sample * ns * steps * comm.world / (ms * 1e-3) / 1e9 / comm.world
+    out = {"metric": "rdf_samples_per_sec", "value": ns * steps * comm.world / (ms * 1e-3), "unit": "samples/s",
+           "n_gpus": comm.world, "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": ms / steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic: uniform random positions of 4000 atoms, boxes 15.2-20.5 (the density range of the 32x32 grid)",
            "config": {"workload": "C5: RDF histogram (lammps_distr.calculate_rdf), N=4000, SBINS=64, %d samples per step per GPU" % ns,
                       "l2": "inputs %.0f MB per step %s L2" % (12e-6 * n * ns, "larger than" if 12 * n * ns > 126e6 else "fit in; compute-bound kernel")},
-           "ordered_pair_distances_per_sec": n * (n - 1.0) * ns * args.steps * comm.world / (ms * 1e-3),
+           "ordered_pair_distances_per_sec": n * (n - 1.0) * ns * steps * comm.world / (ms * 1e-3),
            "e2e": {"value": ns * e2e_steps * comm.world / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": (12 * n + 4) * ns,
                    "d2h_bytes_per_step": 4 * sb * ns, "steps": e2e_steps},
-           "gpu_launches": args.steps * comm.world,
+           "gpu_launches": steps * comm.world,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "kernel": "nmrdf::k_rdf", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                         "note": "algorithmic bytes %d per sample; the kernel is bound by FP32/integer issue (N(N-1) ordered pair distances per sample), not by HBM" % bytes_per_sample},
            "clocks": clocks}
+    # FP32-pipe view: 9 flop per ORDERED pair of the bit-exact formulation (3 sub, 3 mul, 2 add, 1 sqrt)
+    peak32, _ = nm.measure_fma_peak(dev, 32)
+    ach32 = 9.0 * out["ordered_pair_distances_per_sec"] / comm.world
+    out["fp32_pipe"] = {"achieved": ach32 / 1e12, "peak": peak32 / 1e12, "unit": "TFLOP/s", "frac": ach32 / peak32,
+                        "flops": "9 per ordered pair distance (un-contracted float32: 3 sub, 3 mul, 2 add, 1 sqrt); image selection, range tests and binning are overhead",
+                        "peak_source": "live FFMA microbenchmark (nm_measure_fma_peak)"}
+    traffic, capture = ncu_traffic("c5") if comm.world == 1 else (None, None)
+    out["roofline"]["traffic"] = traffic
+    if capture:
+        out["roofline"]["traffic_unit"] = "bytes/launch (ncu --set full, profiles/%s)" % capture
     if comm.world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)

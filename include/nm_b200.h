@@ -139,6 +139,10 @@ int  nm_set_state(nm_engine* h, const double* x, const double* v, const double* 
 int  nm_get_state(nm_engine* h, double* x, double* v, double* box,
                   double* dx, double* dv, double* dt);
 
+/* ---- 'velocity all create T[j] seed dist gaussian' + 'zero linear' + 'zero angular' for every local slot outside a move:
+ *      the draw init_sample leaves in STATE with -is (lammps_remcmc.py:420-425). tag selects the RNG stream. */
+int  nm_velocity_create(nm_engine* h, int64_t tag);
+
 /* ---- thermodynamic labels of the local slots: (et, pf) of init_constant
  *      (lammps_remcmc.py:128-131), T[j] and the '%f'-rounded T LAMMPS receives
  *      in 'velocity all create %f' (:604). Each [n_rep]. */
@@ -226,6 +230,15 @@ int64_t nm_format_traj(int32_t natoms, double box, const double* x, char* buf, i
  * order; out_off[nrep+1] receives the byte offsets. box: [nrep], x: [nrep][3*natoms]. */
 int64_t nm_format_traj_batch(int32_t nrep, int32_t natoms, const double* box, const double* x,
                              char* buf, int64_t cap, int64_t* out_off, int32_t nthreads);
+
+/* ---- N2: streaming writers. One call per recorded cycle appends every local replica's record to its own file
+ *      (open(.., 'a') of write_thrm / write_traj), formatted once; NULL path = format only. pos_out / box_out /
+ *      parsed_out (optional) receive what lammps_parse.py:45,88-93 reads back from that text (decimal -> double ->
+ *      float32), i.e. the contents of the parser's .pos/.box/.<thermo>.npy files. Return bytes written or <0.
+ *      vals: [nrep][17] (write_thrm column order); box: [nrep]; x: [nrep][3*natoms]. */
+int64_t nm_append_traj_batch(int32_t nrep, int32_t natoms, const double* box, const double* x,
+                             const char* const* paths, int32_t nthreads, float* pos_out, float* box_out);
+int64_t nm_append_thrm_batch(int32_t nrep, const double* vals, const char* const* paths, float* parsed_out);
 
 /* ---- roofline denominators: sustained FMA issue rate of this device, measured
  *      with a dependent-chain-free FMA kernel. Returns FLOP/s (2 per FMA). */

@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -75,9 +76,16 @@ struct Dev {
   double *list_pairs;                      // [nrep] listed unordered pairs of the current list
   int *cfg_slot, *slot_cfg;                // local permutation
   unsigned long long* cta_clk;             // [nrep] SM clocks the configuration's CTA spent in the last cycle
+  unsigned long long* cost;                // [nrep][2] last cycle: contention-independent work estimate (listed pairs evaluated + 0.3 N^2 per list
+                                           // build, in units of one listed pair), force evaluations
   unsigned long long* rep_ct;              // [nrep][NM_COUNTER_WIDTH] the last cycle's counters of each configuration
   unsigned long long* mv_clk;              // [nrep][4] last cycle: SM clocks in PMC / VMC / HMC moves (solo-corrected), [3] = moves of each kind packed 3 x 16 bit
-  int* order;                              // [nrep] blockIdx -> configuration (cost-balanced placement)
+  int* order;                              // [nrep] ticket (within a segment) -> configuration, cheapest first
+  int* sched;                              // work queue of the persistent cycle kernel (reset by k_schedule before every launch):
+                                           // [0] next ticket, [1 + c] segments of configuration c that are complete,
+                                           // [1 + nrep] CTAs arrived, [2 + nrep] placement invalid, [3 + nrep + smid] CTAs on SM smid
+  int nseg, seg_moves;                     // a cycle is cut into nseg segments of seg_moves moves (the unit of scheduling)
+  int place;                               // 1: first ticket of every CTA from the SM-aware placement (placement_rank)
   int *status;                             // [nrep]
   // per local slot
   double *label;                           // [nrep][4] et pf temp temp_vel
@@ -577,8 +585,16 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
   }
   __syncthreads();
   // ---- (2) rows
+#ifdef NM_DEBUG_CLOCKS
+  const long long t_rows0 = clock64();
+  if (threadIdx.x == 0) cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)(t_rows0 - t_tiles0);      // tiles + ghost table
+#endif
   int over = 0; double tot = 0.0;
   if (own) { if (ghost) walk_hit_row<true>(d, cx, tid, pi, over, tot); else walk_hit_row<false>(d, cx, tid, pi, over, tot); }
+#ifdef NM_DEBUG_CLOCKS
+  __syncthreads();
+  if (threadIdx.x == 0) cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_rows0);    // row walk (slowest warp)
+#endif
   double r[2] = { tot, (double)over };
   bsum<2>(r, cx);
   cx.list_pairs = 0.5 * r[0];
@@ -848,7 +864,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
   double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
   const long long t_eval0 = clock64();
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
-#ifdef NM_DEBUG_CLOCKS
+#ifdef NM_DEBUG_LOOPCLOCKS
     const long long t_atom0 = clock64();
 #endif
     const double xi = cx.sp[3 * i], yi = cx.sp[3 * i + 1], zi = cx.sp[3 * i + 2];
@@ -905,7 +921,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       cur = nxt;
     }
 #endif
-#ifdef NM_DEBUG_CLOCKS   // per-atom loop clocks of thread 0 (tools/probe.py); compiled out of the product build
+#ifdef NM_DEBUG_LOOPCLOCKS   // per-atom loop clocks of thread 0 (tools/probe.py); compiled out of the product build
     if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(clock64() - t_atom0); cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)nq; }
 #endif
     cx.gf[i] = fx; cx.gf[Npad + i] = fy; cx.gf[2 * Npad + i] = fz;
@@ -1455,67 +1471,163 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
   }
 }
 
-// gen_sample (lammps_remcmc.py:665-691): MOD x move_mc (:643-658), then lammps_extract (:377-391)
+// gen_sample (lammps_remcmc.py:665-691): MOD x move_mc (:643-658), then lammps_extract (:377-391).
+//
+// PERSISTENT kernel with a move-granular work queue. The MOD moves of a configuration form a sequential chain, but the
+// chains differ in cost (a melt rebuilds its list twice per trajectory, a cold solid never; 45 .. 93 M clocks at C2) and
+// there are fewer CTA slots than would balance them: with one CTA per configuration the slowest chain sets the kernel time
+// while SMs that hold a single CTA (which runs 1.6x faster alone) finish early and idle. Here a cycle is cut into nseg
+// SEGMENTS of seg_moves moves. Tickets t = segment * nrep + rank are handed out in order (atomic counter); the CTA that
+// draws (segment s, configuration c) waits until segment s - 1 of c is published (acquire on sched[1 + c]; its ticket is
+// older, hence held by a running CTA: no deadlock as long as every CTA of the grid is resident, which the launch bounds to
+// the occupancy), runs the moves out of shared memory exactly as before, writes the state back and publishes s + 1
+// (release). A configuration thus migrates between CTAs / SMs from segment to segment: whoever is free continues the
+// cheapest unfinished chain, so every SM stays busy to the end of the cycle. The state that crosses a segment boundary is
+// exactly the state that crosses a cycle boundary (positions, box, energies, step counters, list bookkeeping, all in
+// global memory), so results are bit-identical to the unsegmented cycle and independent of the schedule.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+// SM-aware placement (thread 0 of every CTA, once per launch; nsm < nrep <= 2 nsm, two CTAs fit per SM, whole grid resident).
+// The block scheduler deals the CTAs breadth-first: 2 nsm - nrep SMs end up with ONE CTA, which then runs ~1.4x faster than a
+// CTA that shares its SM, and two expensive chains that happen to share an SM set the kernel time. Every CTA registers on
+// its SM (%smid), waits until the whole grid has registered, and derives its rank in the cost order (order[] is sorted most
+// expensive first) from the final occupancy map, the same for everybody: the k-th single-CTA SM takes rank k (the most
+// expensive chains run alone), the k-th shared SM pairs rank nsolo + k with rank nrep - 1 - k (expensive with cheap: the
+// cheap chain ends early and leaves the SM to its partner). Any other occupancy pattern: arrival order.
+constexpr int SMID_MAX = 256;
+static __device__ int placement_rank(const Dev& d) {
+  int* arrived = d.sched + 1 + d.nrep; int* invalid = arrived + 1; int* smcount = arrived + 2;
+  unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  int j = 0;
+  if (smid < (unsigned)SMID_MAX) j = atomicAdd(&smcount[smid], 1); else atomicExch(invalid, 1);
+  __threadfence();
+  const int a = atomicAdd(arrived, 1);
+  while (ld_acquire_gpu(arrived) < (int)gridDim.x) __nanosleep(64);
+  int nsolo = 0, npair = 0, ksolo = 0, kpair = 0, bad = ld_acquire_gpu(invalid);
+  for (int i = 0; i < SMID_MAX; i++) {
+    const int n = ld_acquire_gpu(&smcount[i]);
+    if (n == 1) { nsolo++; if (i < (int)smid) ksolo++; }
+    else if (n == 2) { npair++; if (i < (int)smid) kpair++; }
+    else if (n != 0) bad = 1;
+  }
+  if (bad || nsolo + 2 * npair != d.nrep) return a;
+  const int n_me = ld_acquire_gpu(&smcount[smid]);
+  return n_me == 1 ? ksolo : (j == 0 ? nsolo + kpair : d.nrep - 1 - kpair);
+}
+
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR, NM_CTAS_PER_SM(NTHR))
 k_cycle(Dev d, long long cycle) {
   constexpr bool S32 = NTHR == 1024;
   extern __shared__ __align__(16) unsigned char smem[];
-  Ctx cx; ctx_init(d, cx, d.order[blockIdx.x], smem);
-  const int c = cx.c, slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
-  const long long t_cycle0 = clock64();
-  const double et = d.label[4 * slot], pf = d.label[4 * slot + 1], t_vel = d.label[4 * slot + 3];
-  const double dxs = d.step[3 * c], dvs = d.step[3 * c + 1], dts = d.step[3 * c + 2];
-  load_positions(d, cx);
-  update_thr(d, cx);
-  Energy en = { d.pe[c], d.w[c] };
-  double cnt[6];
-  for (int k = 0; k < 6; k++) cnt[k] = d.cnt[6 * c + k];
-  __syncthreads();
-  unsigned long long kclk[3] = { 0ull, 0ull, 0ull }; unsigned kcnt[3] = { 0u, 0u, 0u };   // per move kind (thread 0)
-  for (int mv = 0; mv < d.mod; mv++) {
-    const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)gslot(d, slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
-    const double roll = rng_uniform(r, 0, P_ROLL);
-    const long long t_mv0 = clock64();
-    const int kind = roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2);
-    if (kind == 0) {
-      if (d.bulk) bulk_position_mc<S32>(d, cx, r, et, dxs, en, cnt);
-      else iter_position_mc<S32>(d, cx, r, et, dxs, en, cnt);
-    } else if (kind == 1) volume_mc<S32>(d, cx, r, et, pf, dvs, en, cnt);
-    else hamiltonian_mc<S32>(d, cx, r, et, t_vel, dts, en, cnt);
-    if (threadIdx.x == 0) { cx.ct[NM_CT_SWEEPS]++; kclk[kind] += (unsigned long long)(clock64() - t_mv0); kcnt[kind]++; }
-  }
-  // lammps_extract
-  double t[1] = { 0 };
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const double vx = cx.gv[i], vy = cx.gv[Npad + i], vz = cx.gv[2 * Npad + i];
-    t[0] += vx * vx + vy * vy + vz * vz;
-  }
-  bsum<1>(t, cx);
-  store_positions(cx);
-  if (threadIdx.x == 0) {
-    const double ke = 0.5 * d.mass * t[0], dof = 3.0 * N - 3.0, temp = 2.0 * ke / dof, vol = pow(cx.L, 3.0);
-    double* th = d.thermo + (size_t)slot * NM_THERMO_WIDTH;
-    th[NM_TH_TEMP] = temp; th[NM_TH_PE] = en.pe; th[NM_TH_KE] = ke;
-    th[NM_TH_VIRIAL] = (dof * temp + en.w) / 3.0 * (1.0 / vol);
-    th[NM_TH_BOX] = cx.L; th[NM_TH_VOL] = vol; th[NM_TH_DX] = dxs; th[NM_TH_DV] = dvs; th[NM_TH_DT] = dts;
-    for (int k = 0; k < 6; k++) { th[NM_TH_NTP + k] = cnt[k]; d.cnt[6 * c + k] = cnt[k]; }
-    for (int k = 0; k < 3; k++) {
-      const float a = (float)cnt[2 * k + 1] / (float)cnt[2 * k];        // float32 ratio, nan_to_num (0/0 -> 0)
-      th[NM_TH_AP + k] = isnan(a) ? 0.0 : (double)a;
+  __shared__ int s_ticket;
+  const int ntickets = d.nseg * d.nrep;
+  bool first = true;
+  for (;;) {
+    __syncthreads();                                  // everybody is done with the previous segment (and its s_ticket)
+    if (threadIdx.x == 0) s_ticket = (first && d.place) ? placement_rank(d) : atomicAdd(&d.sched[0], 1);
+    first = false;
+    __syncthreads();
+    const int ticket = s_ticket;
+    if (ticket >= ntickets) break;
+    const int seg = ticket / d.nrep, c = d.order[ticket - seg * d.nrep];
+    if (seg > 0) {
+      if (threadIdx.x == 0) while (ld_acquire_gpu(&d.sched[1 + c]) < seg) __nanosleep(256);
+      __syncthreads();
     }
-    d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.ke[c] = ke; d.L0[c] = cx.L0; d.L0o[c] = cx.L0o; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs; d.lcur[c] = cx.lbuf;
-    if (cx.status) d.status[c] |= cx.status;
-    cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
-    const unsigned long long dt_cycle = (unsigned long long)(clock64() - t_cycle0);
-    cx.ct[NM_CT_CLK_TOTAL] += dt_cycle;
-    // placement cost: a CTA that had its SM to itself ran ~1.4x faster than it would have next to a neighbour (measured)
-    const bool solo = d.per_sm == 2 && d.nrep > d.nsm && d.nrep <= 2 * d.nsm && (int)blockIdx.x >= d.nrep - d.nsm && (int)blockIdx.x < d.nsm;
-    d.cta_clk[c] = solo ? dt_cycle + dt_cycle * 2 / 5 : dt_cycle;
-    for (int k = 0; k < 3; k++) d.mv_clk[4 * c + k] = solo ? kclk[k] + kclk[k] * 2 / 5 : kclk[k];
-    d.mv_clk[4 * c + 3] = (unsigned long long)min(kcnt[0], 65535u) | ((unsigned long long)min(kcnt[1], 65535u) << 16) | ((unsigned long long)min(kcnt[2], 65535u) << 32);
-    for (int k = 0; k < NM_COUNTER_WIDTH; k++) { d.rep_ct[(size_t)c * NM_COUNTER_WIDTH + k] = cx.ct[k]; if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]); }
+    Ctx cx; ctx_init(d, cx, c, smem);
+    const int slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
+    const long long t_seg0 = clock64();
+    const double et = d.label[4 * slot], pf = d.label[4 * slot + 1], t_vel = d.label[4 * slot + 3];
+    const double dxs = d.step[3 * c], dvs = d.step[3 * c + 1], dts = d.step[3 * c + 2];
+    load_positions(d, cx);
+    update_thr(d, cx);
+    Energy en = { d.pe[c], d.w[c] };
+    double cnt[6];
+    for (int k = 0; k < 6; k++) cnt[k] = d.cnt[6 * c + k];
+    __syncthreads();
+    unsigned long long kclk[3] = { 0ull, 0ull, 0ull }; unsigned kcnt[3] = { 0u, 0u, 0u };   // per move kind (thread 0)
+    const int mv0 = seg * d.seg_moves, mv1 = min(d.mod, mv0 + d.seg_moves);
+    for (int mv = mv0; mv < mv1; mv++) {
+      const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)gslot(d, slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
+      const double roll = rng_uniform(r, 0, P_ROLL);
+      const long long t_mv0 = clock64();
+      const int kind = roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2);
+      if (kind == 0) {
+        if (d.bulk) bulk_position_mc<S32>(d, cx, r, et, dxs, en, cnt);
+        else iter_position_mc<S32>(d, cx, r, et, dxs, en, cnt);
+      } else if (kind == 1) volume_mc<S32>(d, cx, r, et, pf, dvs, en, cnt);
+      else hamiltonian_mc<S32>(d, cx, r, et, t_vel, dts, en, cnt);
+      if (threadIdx.x == 0) { cx.ct[NM_CT_SWEEPS]++; kclk[kind] += (unsigned long long)(clock64() - t_mv0); kcnt[kind]++; }
+    }
+    const bool last = seg == d.nseg - 1;
+    double t[1] = { 0 };
+    if (last) {                                         // lammps_extract
+      for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        const double vx = cx.gv[i], vy = cx.gv[Npad + i], vz = cx.gv[2 * Npad + i];
+        t[0] += vx * vx + vy * vy + vz * vz;
+      }
+      bsum<1>(t, cx);
+    }
+    store_positions(cx);
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 6; k++) d.cnt[6 * c + k] = cnt[k];
+      if (last) {
+        const double ke = 0.5 * d.mass * t[0], dof = 3.0 * N - 3.0, temp = 2.0 * ke / dof, vol = pow(cx.L, 3.0);
+        double* th = d.thermo + (size_t)slot * NM_THERMO_WIDTH;
+        th[NM_TH_TEMP] = temp; th[NM_TH_PE] = en.pe; th[NM_TH_KE] = ke;
+        th[NM_TH_VIRIAL] = (dof * temp + en.w) / 3.0 * (1.0 / vol);
+        th[NM_TH_BOX] = cx.L; th[NM_TH_VOL] = vol; th[NM_TH_DX] = dxs; th[NM_TH_DV] = dvs; th[NM_TH_DT] = dts;
+        for (int k = 0; k < 6; k++) th[NM_TH_NTP + k] = cnt[k];
+        for (int k = 0; k < 3; k++) {
+          const float a = (float)cnt[2 * k + 1] / (float)cnt[2 * k];        // float32 ratio, nan_to_num (0/0 -> 0)
+          th[NM_TH_AP + k] = isnan(a) ? 0.0 : (double)a;
+        }
+        d.ke[c] = ke;
+      }
+      d.box[c] = cx.L; d.pe[c] = en.pe; d.w[c] = en.w; d.L0[c] = cx.L0; d.L0o[c] = cx.L0o; d.micmode[c] = cx.mic; d.list_pairs[c] = cx.list_pairs; d.lcur[c] = cx.lbuf;
+      if (cx.status) d.status[c] |= cx.status;
+      cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
+#ifdef NM_DEBUG_SMID
+      { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); cx.ct[NM_CT_RESERVED] = smid; }
+#endif
+      const unsigned long long dt_seg = (unsigned long long)(clock64() - t_seg0);
+      cx.ct[NM_CT_CLK_TOTAL] += dt_seg;
+      // per-configuration bookkeeping of the cycle (cost ranks for the next schedule, diagnostics): reset by segment 0
+      const unsigned long long old_cnt = seg ? d.mv_clk[4 * c + 3] : 0ull;
+      d.cta_clk[c] = (seg ? d.cta_clk[c] : 0ull) + dt_seg;
+      d.cost[2 * c] = (seg ? d.cost[2 * c] : 0ull) + cx.ct[NM_CT_LIST_PAIRS] + cx.ct[NM_CT_LIST_BUILDS] * (unsigned long long)(0.3 * N * N);
+      d.cost[2 * c + 1] = (seg ? d.cost[2 * c + 1] : 0ull) + cx.ct[NM_CT_FORCE_EVALS];
+      for (int k = 0; k < 3; k++) d.mv_clk[4 * c + k] = (seg ? d.mv_clk[4 * c + k] : 0ull) + kclk[k];
+      unsigned long long packed = 0ull;
+      for (int k = 0; k < 3; k++) packed |= (unsigned long long)min((unsigned)((old_cnt >> (16 * k)) & 0xffffull) + kcnt[k], 65535u) << (16 * k);
+      d.mv_clk[4 * c + 3] = packed;
+      for (int k = 0; k < NM_COUNTER_WIDTH; k++) {
+        d.rep_ct[(size_t)c * NM_COUNTER_WIDTH + k] = (seg ? d.rep_ct[(size_t)c * NM_COUNTER_WIDTH + k] : 0ull) + cx.ct[k];
+        if (cx.ct[k]) atomicAdd(&d.counters[k], cx.ct[k]);
+      }
+    }
+    __threadfence();                                    // this thread's state writes are visible device-wide ...
+    __syncthreads();                                    // ... for every thread of the CTA, before thread 0 publishes the segment
+    if (threadIdx.x == 0) st_release_gpu(&d.sched[1 + c], seg + 1);
   }
+}
+
+// 'velocity all create T seed dist gaussian' + zero linear + zero angular on the resident configurations, outside a move:
+// the draw the reference's init_sample keeps in STATE with -is (lammps_remcmc.py:420-425; the 'run 1024' that follows has no
+// integrator defined and changes nothing). Stream: (seed, global slot, move counter 2^64 - 1 - tag).
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, NM_CTAS_PER_SM(NTHR))
+k_velinit(Dev d, long long tag) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Ctx cx; ctx_init(d, cx, blockIdx.x, smem);
+  const int slot = d.cfg_slot[cx.c];
+  load_positions(d, cx);
+  __syncthreads();
+  const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)gslot(d, slot), ~0ull - (uint64_t)tag);
+  const double ke = velocity_create(d, cx, r, d.label[4 * slot + 3]);
+  if (threadIdx.x == 0) d.ke[cx.c] = ke;
 }
 
 // ---- launchers, one set per thread count. build.py compiles this file four times (-DNM_TU=256 / 512 / 1024: the
@@ -1525,15 +1637,20 @@ k_cycle(Dev d, long long cycle) {
   cudaError_t set_smem_##T(size_t sm) {                                                                              \
     cudaError_t e = cudaFuncSetAttribute(k_cycle<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);          \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eval<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_velinit<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
     return e;                                                                                                        \
   }                                                                                                                  \
-  void launch_cycle_##T(const Dev& d, long long cycle, size_t sm, cudaStream_t st) { k_cycle<T><<<d.nrep, T, sm, st>>>(d, cycle); } \
+  void launch_cycle_##T(const Dev& d, long long cycle, int grid, size_t sm, cudaStream_t st) { k_cycle<T><<<grid, T, sm, st>>>(d, cycle); } \
+  int occupancy_##T(size_t sm) { int n = 0; return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cycle<T>, T, sm) == cudaSuccess ? n : 1; } \
+  void launch_velinit_##T(const Dev& d, long long tag, size_t sm, cudaStream_t st) { k_velinit<T><<<d.nrep, T, sm, st>>>(d, tag); } \
   void launch_eval_##T(const Dev& d, double* pe, double* w, double* f, long long* np_, size_t sm, cudaStream_t st) { \
     k_eval<T><<<d.nrep, T, sm, st>>>(d, pe, w, f, np_);                                                              \
   }
 #define NM_LAUNCHER_DECLS(T)                                                                                         \
   cudaError_t set_smem_##T(size_t sm);                                                                               \
-  void launch_cycle_##T(const Dev& d, long long cycle, size_t sm, cudaStream_t st);                                  \
+  void launch_cycle_##T(const Dev& d, long long cycle, int grid, size_t sm, cudaStream_t st);                        \
+  int occupancy_##T(size_t sm);                                                                                      \
+  void launch_velinit_##T(const Dev& d, long long tag, size_t sm, cudaStream_t st);                                  \
   void launch_eval_##T(const Dev& d, double* pe, double* w, double* f, long long* np_, size_t sm, cudaStream_t st);
 NM_LAUNCHER_DECLS(256) NM_LAUNCHER_DECLS(512) NM_LAUNCHER_DECLS(1024)
 #if !defined(NM_TU) || NM_TU == 256
@@ -1547,33 +1664,31 @@ NM_LAUNCHERS(1024)
 #endif
 
 #if !defined(NM_TU) || NM_TU == 0
-// Cost-balanced CTA placement for the next cycle. Blocks b and b + nsm share an SM when two CTAs fit per SM and
-// nrep <= 2 nsm (the block scheduler fills SMs round-robin). With last cycle's per-configuration clocks sorted in
-// descending order, the nsm-(nrep-nsm) SMs that hold a single CTA get the most expensive configurations and every
-// other SM pairs an expensive with a cheap one. Larger grids are launched in descending cost (longest first).
-__global__ void k_schedule(Dev d, int nsm, int per_sm, long long cycle) {
+// Queue set-up for the next cycle: reset the ticket counter, the per-configuration progress and the SM occupancy map, and rank
+// the configurations by predicted cost. One segment per cycle (default): most expensive first (SM-aware placement, or
+// longest-first tickets when there are more configurations than CTA slots). Several segments (NM_SEG_MOVES): cheapest
+// first, so that the k-th CTA to become free continues the k-th cheapest chain, whose previous segment is the k-th to
+// have finished (short waits).
+__global__ void k_schedule(Dev d, long long cycle, int do_sort) {
   extern __shared__ unsigned long long sclk[];
   int* sorted = reinterpret_cast<int*>(sclk + d.nrep);
-  // predicted cost of the coming cycle: the move kinds are known in advance (counter-based RNG: the same rolls
-  // k_cycle will draw), the cost of a move of each kind is last cycle's average for this configuration
+  for (int c = threadIdx.x; c < 3 + d.nrep + SMID_MAX; c += blockDim.x) d.sched[c] = (c == 0 && d.place) ? d.nrep : 0;   // placement hands out the first nrep tickets
+  if (!do_sort) { for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) d.order[c] = c; return; }
+  // predicted cost of the coming cycle: last cycle's work estimate of the configuration (listed pairs evaluated + list builds:
+  // independent of which SM it ran on and with whom), scaled by the number of force evaluations the coming cycle will make
+  // -- the move kinds are known in advance (counter-based RNG: the same rolls k_cycle will draw)
   for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) {
-    const unsigned long long packed = d.mv_clk[4 * c + 3], total = d.cta_clk[c];
-    const unsigned last[3] = { (unsigned)(packed & 0xffffull), (unsigned)((packed >> 16) & 0xffffull), (unsigned)((packed >> 32) & 0xffffull) };
-    const unsigned nlast = last[0] + last[1] + last[2];
-    unsigned long long cost = total;
-    if (nlast) {
-      unsigned n[3] = { 0u, 0u, 0u };
+    unsigned long long cost = d.cost[2 * c];
+    const unsigned long long evals_last = d.cost[2 * c + 1];
+    if (evals_last) {
+      unsigned long long evals = 0;
       const int slot = d.cfg_slot[c];
       for (int mv = 0; mv < d.mod; mv++) {
         const Rng r = rng_make(d.seed_lo, d.seed_hi, (uint32_t)gslot(d, slot), (uint64_t)cycle * (uint64_t)d.mod + (uint64_t)mv);
         const double roll = rng_uniform(r, 0, P_ROLL);
-        n[roll <= d.ppos ? 0 : (roll <= (d.ppos + d.pvol) ? 1 : 2)]++;
+        evals += roll <= d.ppos + d.pvol ? 1 : d.nstps;
       }
-      cost = 0ull;
-      for (int k = 0; k < 3; k++) {
-        const unsigned long long per = last[k] ? d.mv_clk[4 * c + k] / last[k] : total / nlast;   // kind not seen last cycle: the mean move
-        cost += per * n[k];
-      }
+      cost = (unsigned long long)((double)cost * (double)evals / (double)evals_last);
     }
     sclk[c] = cost;
   }
@@ -1581,20 +1696,9 @@ __global__ void k_schedule(Dev d, int nsm, int per_sm, long long cycle) {
   for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) {
     const unsigned long long v = sclk[c];
     int rank = 0;
-    for (int o = 0; o < d.nrep; o++) rank += (sclk[o] > v) || (sclk[o] == v && o < c);
-    sorted[rank] = c;
-  }
-  __syncthreads();
-  const int n = d.nrep;
-  for (int b = threadIdx.x; b < n; b += blockDim.x) {
-    int pick = b;
-    if (per_sm == 2 && n > nsm && n <= 2 * nsm) {
-      const int npair = n - nsm, nsingle = nsm - npair;
-      if (b < npair) pick = nsingle + b;                 // first CTA of a shared SM: next most expensive
-      else if (b < nsm) pick = b - npair;                // SM with a single CTA: the most expensive ones
-      else pick = n - 1 - (b - nsm);                     // second CTA of shared SM (b - nsm): the cheapest
-    }
-    d.order[b] = sorted[pick];
+    if (d.nseg > 1) { for (int o = 0; o < d.nrep; o++) rank += (sclk[o] < v) || (sclk[o] == v && o < c); }      // cheapest first
+    else { for (int o = 0; o < d.nrep; o++) rank += (sclk[o] > v) || (sclk[o] == v && o < c); }                   // one segment: longest first
+    d.order[rank] = c;
   }
 }
 
@@ -1728,7 +1832,7 @@ struct nm_engine {
   nm_config cfg;
   Dev d;
   cudaStream_t stream; bool own_stream;
-  int threads; size_t smem; int nsm;
+  int threads; size_t smem; int nsm; int grid;   // grid: CTAs of the persistent cycle kernel (all resident)
   std::vector<void*> allocs;
   double *stage_a, *stage_b, *stage_s;     // device staging: x/v AoS [nrep][3N], scalars [nrep][8]
   double *ex_table, *ex_uni, *ex_scratch; int *ex_perm, *ex_tmp; unsigned long long* ex_swaps;
@@ -1812,7 +1916,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   d.small = N <= NSMALL;
   h->smem = smem_bytes(d.Npad, N, d.small, h->threads);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, cfg->device) == cudaSuccess) h->nsm = pr.multiProcessorCount; else h->nsm = 148; }
-  d.nsm = h->nsm; d.per_sm = ((h->smem + 1024) * 2 <= 227 * 1024 && h->threads <= 512) ? 2 : 1;
+  d.nsm = h->nsm; d.per_sm = 1;
   if (h->smem > 227 * 1024) { nm_destroy(h); return fail(NM_EINVAL, "nm_create: natoms %d needs %zu B of shared memory per CTA (> 227 KB)", N, h->smem); }
   const size_t per = (size_t)nrep * 3 * d.Npad;
   DA(d.x, per); DA(d.v, per); DA(d.f, per); DA(d.xs, per); DA(d.vs, per); DA(d.fs, per); DA(d.x0, 2 * per);
@@ -1823,7 +1927,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
-  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep);
+  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.cost, 2 * (size_t)nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep); DA(d.sched, (size_t)nrep + 3 + SMID_MAX);
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
@@ -1845,6 +1949,22 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   const int sm = (int)h->smem;
   e = h->threads == 256 ? set_smem_256(h->smem) : (h->threads == 512 ? set_smem_512(h->smem) : set_smem_1024(h->smem));
   if (e != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "cudaFuncSetAttribute(smem=%zu): %s", h->smem, cudaGetErrorString(e)); }
+  {
+    // persistent cycle kernel: every CTA of the grid must be resident (a CTA may wait for a segment held by another one)
+    int occ = h->threads == 256 ? occupancy_256(h->smem) : (h->threads == 512 ? occupancy_512(h->smem) : occupancy_1024(h->smem));
+    if (occ < 1) occ = 1;
+    d.per_sm = occ;
+    const long long slots = (long long)occ * h->nsm;
+    h->grid = (int)(nrep < slots ? nrep : slots);
+    // segment length: NM_SEG_MOVES moves (default: the whole cycle in one segment; measured at C2: 4-move segments
+    // without placement 46.2 ms, one segment 49 ms, SM-aware placement of whole cycles: see DESIGN 4.1)
+    int seg_moves = 0;
+    if (const char* ev = getenv("NM_SEG_MOVES")) seg_moves = atoi(ev);
+    if (seg_moves <= 0 || seg_moves > d.mod) seg_moves = d.mod > 0 ? d.mod : 1;
+    d.seg_moves = seg_moves;
+    d.nseg = d.mod > 0 ? (d.mod + seg_moves - 1) / seg_moves : 1;
+    d.place = occ == 2 && nrep > h->nsm && nrep <= slots && h->nsm <= SMID_MAX && !getenv("NM_NO_PLACEMENT");
+  }
   *out = h;
   return NM_OK;
 }
@@ -1966,17 +2086,30 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   if (!h) return fail(NM_EINVAL, "null engine");
   if (!h->have_state || !h->have_labels) return fail(NM_ESTATE, "nm_run_cycle: state and labels must be uploaded first");
   CK(cudaSetDevice(h->cfg.device));
-  if (h->d.nrep > h->nsm && h->d.nrep <= 4096) {        // placement from the last cycle's clocks and this cycle's move kinds
-    k_schedule<<<1, 1024, h->d.nrep * (sizeof(unsigned long long) + sizeof(int)), h->stream>>>(h->d, h->nsm, h->d.per_sm, (long long)cycle);
+  {                                                       // queue reset + cost ranks from the last cycle's clocks and this cycle's move kinds
+    const int do_sort = h->d.nrep > 1 && h->d.nrep <= 4096 && (h->d.nseg > 1 || h->d.nrep > h->nsm);
+    k_schedule<<<1, 1024, do_sort ? h->d.nrep * (sizeof(unsigned long long) + sizeof(int)) : 0, h->stream>>>(h->d, (long long)cycle, do_sort);
     h->launches++;
     CK(cudaGetLastError());
   }
-  if (h->threads == 256) launch_cycle_256(h->d, (long long)cycle, h->smem, h->stream);
-  else if (h->threads == 512) launch_cycle_512(h->d, (long long)cycle, h->smem, h->stream);
-  else launch_cycle_1024(h->d, (long long)cycle, h->smem, h->stream);
+  if (h->threads == 256) launch_cycle_256(h->d, (long long)cycle, h->grid, h->smem, h->stream);
+  else if (h->threads == 512) launch_cycle_512(h->d, (long long)cycle, h->grid, h->smem, h->stream);
+  else launch_cycle_1024(h->d, (long long)cycle, h->grid, h->smem, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   h->have_thermo = true;
+  return NM_OK;
+}
+
+int nm_velocity_create(nm_engine* h, int64_t tag) {
+  if (!h) return fail(NM_EINVAL, "null engine");
+  if (!h->have_state || !h->have_labels) return fail(NM_ESTATE, "nm_velocity_create: state and labels must be uploaded first");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->threads == 256) launch_velinit_256(h->d, (long long)tag, h->smem, h->stream);
+  else if (h->threads == 512) launch_velinit_512(h->d, (long long)tag, h->smem, h->stream);
+  else launch_velinit_1024(h->d, (long long)tag, h->smem, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
   return NM_OK;
 }
 

@@ -78,6 +78,13 @@ def load_library():
                                 C.c_void_p, C.c_int32, C.c_void_p]
     L.nm_cdf_counts.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                 C.c_void_p, C.c_int32, C.c_void_p]
+    L.nm_velocity_create.argtypes = [C.c_void_p, C.c_int64]
+    L.nm_format_traj_batch.restype = C.c_int64
+    L.nm_format_traj_batch.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+    L.nm_append_traj_batch.restype = C.c_int64
+    L.nm_append_traj_batch.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.nm_append_thrm_batch.restype = C.c_int64
+    L.nm_append_thrm_batch.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.nm_format_thrm.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.nm_format_traj.argtypes = [C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int64]
     L.nm_measure_fma_peak.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -186,6 +193,10 @@ class Engine:
         et, pf, temp_vel = _f64(et, sh), _f64(pf, sh), _f64(temp_vel, sh)
         self._labels = (et.copy(), pf.copy())
         _check(self._L.nm_set_labels(self._h, _ptr(et), _ptr(pf), _ptr(temp), _ptr(temp_vel)))
+
+    def velocity_create(self, tag=0):
+        """draw velocities at every slot's temperature (LAMMPS 'velocity create' + zero linear + zero angular)"""
+        _check(self._L.nm_velocity_create(self._h, int(tag)))
 
     # -- a-1
     def eval(self, want_forces=True):
@@ -324,6 +335,39 @@ def format_traj(natoms, box, x):
     buf = C.create_string_buffer(n + 1)
     L.nm_format_traj(natoms, float(box), _ptr(x), buf, n + 1)
     return buf.raw[:n]
+
+
+def _path_array(paths):
+    arr = (C.c_char_p * len(paths))()
+    for k, p in enumerate(paths):
+        arr[k] = None if p is None else os.fsencode(p)
+    return arr
+
+
+def append_traj_batch(natoms, box, x, paths, nthreads=1, parse_back=False):
+    """append one write_traj record per replica to paths[k] (None: format only); with parse_back also returns the float32
+    (pos, box) lammps_parse.py would read from that text"""
+    box = _f64(box)
+    nrep = box.size
+    x = _f64(x, (nrep, 3 * natoms))
+    pos = np.empty((nrep, natoms, 3), dtype=np.float32) if parse_back else None
+    bx = np.empty(nrep, dtype=np.float32) if parse_back else None
+    n = load_library().nm_append_traj_batch(nrep, natoms, _ptr(box), _ptr(x), _path_array(paths), int(nthreads), _ptr(pos), _ptr(bx))
+    if n < 0:
+        raise NmError(int(n), load_library().nm_last_error().decode(errors="replace"))
+    return pos, bx
+
+
+def append_thrm_batch(vals17, paths, parse_back=False):
+    vals17 = _f64(vals17)
+    nrep = vals17.shape[0]
+    if vals17.shape != (nrep, 17):
+        raise ValueError("vals17 must be (nrep, 17)")
+    out = np.empty((nrep, 17), dtype=np.float32) if parse_back else None
+    n = load_library().nm_append_thrm_batch(nrep, _ptr(vals17), _path_array(paths), _ptr(out))
+    if n < 0:
+        raise NmError(int(n), load_library().nm_last_error().decode(errors="replace"))
+    return out
 
 
 def measure_fma_peak(device=0, precision=64):

@@ -9,12 +9,17 @@ by lammps_parse.py) and <prefix>.rstrt.%04d.npy restart dumps (:821-828). The pe
 work (:394-691) happens inside the CUDA engine (neuralmelting_b200.engine); no LAMMPS, Dask, numba
 or CPU fallback is involved.
 
-Multi-GPU: one process per GPU (torchrun); each rank owns whole pressure rows. The exchange
-all-gathers (pe + ke, vol) of every replica over NCCL and every rank replays the same sweep.
+Multi-GPU: one process per GPU (torchrun); pressure row u lives on rank u mod G (all temperatures of a row together:
+exchanges never cross rows, so every rank decides its own swaps). (pe + ke, vol) of every replica is all-gathered over
+NCCL asynchronously, off the critical path, for the job-wide log. Output is streamed: every recorded cycle is appended
+to per-replica files by a writer thread (bounded memory) and consolidated by concatenation at the end.
 """
 import argparse
 import os
+import queue
+import shutil
 import sys
+import threading
 
 import numpy as np
 
@@ -65,11 +70,15 @@ _FLAGS = [
     ("-dx", "--pos_displace", dict(type=float, default=0.03125, help="position displacement (lattice proportion)")),
     ("-dv", "--vol_displace", dict(type=float, default=0.03125, help="logarithmic volume displacement")),
 ]
+# not in the reference: also write what lammps_parse.py would produce (.pos/.box/.natoms/.<thermo>.npy) during the run
+_EXTRA_FLAGS = [
+    ("-dn", "--direct_npy", dict(action="store_true", help="also emit the parser's .npy files directly (same 5-digit rounding)")),
+]
 
 
 def build_parser():
     parser = argparse.ArgumentParser(description="replica-exchange NPT Monte Carlo on B200 (lammps_remcmc.py drop-in)")
-    for short, long_, kw in _FLAGS:
+    for short, long_, kw in _FLAGS + _EXTRA_FLAGS:
         parser.add_argument(short, long_, **kw)
     return parser
 
@@ -146,29 +155,33 @@ def relaxed_boxes(pressures, sz, device=0):
     return 0.5 * (lo + hi)
 
 
-def init_samples(P, T, sz, dx, rng, interpolate=False, device=0):
-    """init_sample for every slot (lammps_remcmc.py:394-456): relaxed fcc at P[i], then 'displace_atoms all random'
-    by +-DX*LAT (text-rounded) per axis; velocities zero. With -is the log-volume is raised by 0.75 (j+1)/NT
-    (:412); the reference's subsequent 'run 1024' has no integrator defined and leaves positions unchanged."""
+def init_samples(P, T, sz, dx, seed, slots=None, interpolate=False, device=0):
+    """init_sample for the given global slots k = i*NT + j (default: all; lammps_remcmc.py:394-456): relaxed fcc at P[i], then
+    'displace_atoms all random' by +-DX*LAT (text-rounded) per axis; velocities zero (with -is the caller draws them on
+    the GPU: nm_velocity_create). With -is the log-volume is raised by 0.75 (j+1)/NT (:412); the reference's subsequent
+    'run 1024' has no integrator defined and leaves positions unchanged. The displacement stream of a slot is keyed on
+    (seed, k): the start configuration does not depend on how the grid is spread over GPUs."""
     frac = fcc_fractional(sz)
     n = frac.shape[0]
-    boxes_p = relaxed_boxes(P.astype(np.float64), sz, device=device)
     nt = T.size
-    ns = P.size * nt
-    x = np.empty((ns, 3 * n))
-    box = np.empty(ns)
+    slots = np.arange(P.size * nt) if slots is None else np.asarray(slots)
+    rows = np.unique(slots // nt)
+    boxes_p = dict(zip(rows.tolist(), relaxed_boxes(P.astype(np.float64)[rows], sz, device=device)))
+    x = np.empty((slots.size, 3 * n))
+    box = np.empty(slots.size)
     d = text6(dx * LAT["LJ"][1])
-    for k in range(ns):
+    for q, k in enumerate(slots.tolist()):
         i, j = divmod(k, nt)
         L = boxes_p[i]
+        rng = np.random.default_rng([int(seed), 1, k])
         pos = frac * L + d * 2.0 * (rng.random((n, 3)) - 0.5)
         pos -= np.floor(pos / L) * L
         if interpolate:
             Lnew = np.cbrt(np.exp(np.log(L ** 3) + 0.75 * (j + 1) / nt))
             pos *= Lnew / L
             L = text6(Lnew)
-        x[k] = pos.reshape(-1)
-        box[k] = L
+        x[q] = pos.reshape(-1)
+        box[q] = L
     return x, np.zeros_like(x), box
 
 
@@ -206,22 +219,119 @@ def thrm_line(th_row):
 
 
 def traj_records(natoms, box, x, nthreads=1):
-    """write_traj (lammps_remcmc.py:248-256) for a batch of replicas: list of bytes, one record per replica"""
+    """write_traj (lammps_remcmc.py:248-256) for a batch of replicas: list of bytes, one record per replica (formatted once
+    into a buffer sized by the per-record upper bound)"""
     import ctypes as C
     L = nm.load_library()
     nrep = box.size
     x = np.ascontiguousarray(x, dtype=np.float64)
     box = np.ascontiguousarray(box, dtype=np.float64)
     off = np.zeros(nrep + 1, dtype=np.int64)
-    L.nm_format_traj_batch.restype = C.c_int64
-    L.nm_format_traj_batch.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
-    total = L.nm_format_traj_batch(nrep, natoms, box.ctypes.data, x.ctypes.data, None, 0, off.ctypes.data, nthreads)
+    cap = nrep * (96 + natoms * (3 * 13 + 1)) + 1
+    buf = C.create_string_buffer(cap)
+    total = L.nm_format_traj_batch(nrep, natoms, box.ctypes.data, x.ctypes.data, buf, cap, off.ctypes.data, nthreads)
     if total < 0:
         raise nm.NmError(int(total), L.nm_last_error().decode())
-    buf = C.create_string_buffer(int(total) + 1)
-    L.nm_format_traj_batch(nrep, natoms, box.ctypes.data, x.ctypes.data, buf, int(total) + 1, off.ctypes.data, nthreads)
     raw = buf.raw
     return [raw[off[k]:off[k + 1]] for k in range(nrep)]
+
+
+THERMO_NAMES = ("temp", "pe", "ke", "virial", "vol", "dx", "dv", "dt", "ntp", "nap", "ntv", "nav", "nth", "nah", "ap", "av", "ah")
+
+
+def replica_prefix(name, el, i, j):
+    """file_prefix(i, j) of the reference (lammps_remcmc.py:148-151): the per-replica files written during the run"""
+    return os.path.join(os.getcwd(), "%s.%s.%s.%02d.%02d.lammps" % (name, el.lower(), LAT[el][0], i, j))
+
+
+class StreamWriter:
+    """write_outputs (lammps_remcmc.py:259-286) as a pipeline stage: the main loop hands over one recorded cycle (thermo rows,
+    boxes, positions of the local slots) and goes on with the next cycle; a writer thread formats it once (native, threaded)
+    and appends it to the per-replica .thrm / .traj files, as the reference does, so a crash loses nothing that was recorded
+    and host memory stays flat (at most `depth` cycles in flight). With direct_npy the same pass fills memory-mapped
+    .pos/.box/.natoms/.<thermo>.npy files with the values lammps_parse.py:37-103 would read back from the text."""
+
+    def __init__(self, args, pref, slots, npn, ntn, natoms, nrec, headers, nthreads=1, direct_npy=False, create=True, depth=2):
+        self.slots = np.asarray(slots)
+        self.natoms, self.nthreads, self.nrec = natoms, max(1, nthreads), nrec
+        ij = [divmod(int(k), ntn) for k in self.slots]
+        self.thrm_paths = [replica_prefix(args.name, args.element, i, j) + ".thrm" for i, j in ij]
+        self.traj_paths = [replica_prefix(args.name, args.element, i, j) + ".traj" for i, j in ij]
+        for p_thrm, p_traj, head in zip(self.thrm_paths, self.traj_paths, headers):
+            with open(p_thrm, "wb") as fh:          # init_output + init_header: start clean (the stale-.traj bug is dropped)
+                fh.write(head)
+            open(p_traj, "wb").close()
+        self.npy = None
+        if direct_npy and nrec > 0:
+            from numpy.lib.format import open_memmap
+            def mm(suffix, dtype, shape):
+                return open_memmap(pref + suffix, mode="w+", dtype=dtype, shape=shape) if create else open_memmap(pref + suffix, mode="r+")
+            self.npy = dict(pos=mm(".pos.npy", np.float32, (npn, ntn, nrec, natoms, 3)), box=mm(".box.npy", np.float32, (npn * ntn * nrec,)),
+                            natoms=mm(".natoms.npy", np.uint16, (npn, ntn, nrec)))
+            for name in THERMO_NAMES:
+                self.npy[name] = mm(".%s.npy" % name, np.float32, (npn, ntn, nrec))
+            self.ntn = ntn
+        self.count = 0
+        self.err = None
+        self.q = queue.Queue(maxsize=depth)
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            if self.err is not None:
+                continue
+            try:
+                self._write(*item)
+            except Exception as e:          # surfaced by the next put() / close()
+                self.err = e
+
+    def _write(self, s, th17, box, x):
+        want = self.npy is not None
+        parsed = nm.append_thrm_batch(th17, self.thrm_paths, parse_back=want)
+        pos, bx = nm.append_traj_batch(self.natoms, box, x, self.traj_paths, nthreads=self.nthreads, parse_back=want)
+        if want:
+            i, j = np.divmod(self.slots, self.ntn)
+            self.npy["pos"][i, j, s] = pos
+            self.npy["box"][self.slots * self.nrec + s] = bx
+            self.npy["natoms"][i, j, s] = self.natoms
+            for c, name in enumerate(THERMO_NAMES):
+                self.npy[name][i, j, s] = parsed[:, c]
+
+    def put(self, thermo, box, x):
+        """thermo: (nloc, 18) records of the cycle; box (nloc,), x (nloc, 3 natoms). The arrays are owned by the writer afterwards."""
+        if self.err is not None:
+            raise self.err
+        self.q.put((self.count, np.ascontiguousarray(thermo[:, _THRM_COLS]), box, x))
+        self.count += 1
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        if self.npy is not None:
+            for a in self.npy.values():
+                a.flush()
+            self.npy = None
+        if self.err is not None:
+            raise self.err
+
+
+def consolidate_outputs(args, pref, npn, ntn):
+    """consolidate_outputs (lammps_remcmc.py:289-316): the per-replica files concatenated in pressure-major, temperature order
+    (streamed, no whole-file reads), then removed"""
+    for ext in (".thrm", ".traj"):
+        with open(pref + ext, "wb") as out:
+            for i in range(npn):
+                for j in range(ntn):
+                    with open(replica_prefix(args.name, args.element, i, j) + ext, "rb") as fh:
+                        shutil.copyfileobj(fh, out, 1 << 22)
+    for i in range(npn):
+        for j in range(ntn):
+            for ext in (".thrm", ".traj"):
+                os.remove(replica_prefix(args.name, args.element, i, j) + ext)
 
 
 # ----------------------------------------------------------------------------- restart files (N4)
@@ -263,33 +373,87 @@ class Comm:
             import torch
             import torch.distributed as dist
             if not dist.is_initialized():
-                backend = "nccl" if torch.cuda.is_available() else "gloo"
+                # NM_DIST_BACKEND=gloo: several ranks on ONE GPU (tests); NCCL needs one device per rank
+                backend = os.environ.get("NM_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
                 if backend == "nccl":
                     torch.cuda.set_device(self.local_rank)
                 dist.init_process_group(backend=backend)
             self.dist = dist
+        self.backend = self.dist.get_backend() if self.dist is not None else None
 
     def row_shard(self, npn):
-        """contiguous blocks of whole pressure rows; exchanges never cross rows (lammps_remcmc.py:782-789)"""
+        """pressure row u lives on rank u mod G: every rank holds an even mix of low- and high-pressure rows
+        and all temperatures of each; exchanges never cross rows (lammps_remcmc.py:782-789). Returns the global rows of this rank."""
         if npn % self.world:
             raise ValueError("pressure_number (%d) must be a multiple of the number of GPUs (%d)" % (npn, self.world))
-        per = npn // self.world
-        return self.rank * per, per
+        return list(range(self.rank, npn, self.world))
 
     def barrier(self):
         if self.dist is not None:
             self.dist.barrier()
 
 
-def allgather_table(comm, eng, torch):
-    """(pe + ke, vol) of every slot in the job: nm_exchange_pack on each rank + one all-gather (16 bytes per replica)"""
-    local = torch.empty((eng.n_rep, 2), dtype=torch.float64, device="cuda")
-    eng.exchange_pack(local.data_ptr())
-    if comm.world == 1:
-        return local
-    full = torch.empty((eng.n_rep_global, 2), dtype=torch.float64, device="cuda")
-    comm.dist.all_gather_into_tensor(full, local)
-    return full
+class TableGather:
+    """(pe + ke, vol) of every slot in the job -- what the reference's client holds in STATE -- kept current OFF the
+    critical path: every rank packs its slots (nm_exchange_pack) and one asynchronous all-gather (16 bytes per replica,
+    NCCL over NVLink) runs beside the next cycle; the swaps themselves are decided locally. latest() returns the most
+    recent completed job-wide table in global slot order."""
+
+    def __init__(self, comm, eng, torch):
+        self.comm, self.eng, self.torch = comm, eng, torch
+        on_gpu = torch.cuda.is_available()
+        coll = "cuda" if on_gpu and getattr(comm, "backend", None) != "gloo" else "cpu"      # where the collective runs
+        self.stage = [torch.empty((eng.n_rep, 2), dtype=torch.float64, device="cuda") for _ in range(2)] if on_gpu and coll == "cpu" else None
+        self.local = [torch.empty((eng.n_rep, 2), dtype=torch.float64, device=coll) for _ in range(2)]
+        self.full = [torch.empty((comm.world, eng.n_rep, 2), dtype=torch.float64, device=coll) for _ in range(2)]
+        self.work = [None, None]
+        self.cur = 0
+        nrow = eng.n_rep // eng.nt
+        # rank r, local row lr -> global row r + lr * world
+        self.order = np.array([(r + lr * comm.world) * eng.nt + j for r in range(comm.world) for lr in range(nrow) for j in range(eng.nt)])
+
+    def start(self):
+        b = self.cur = self.cur ^ 1
+        if self.work[b] is not None:
+            self.work[b].wait()
+        if self.stage is not None:              # gloo with a GPU engine: pack on the device, collective on the host
+            self.eng.exchange_pack(self.stage[b].data_ptr())
+            self.local[b].copy_(self.stage[b])
+        else:
+            self.eng.exchange_pack(self.local[b].data_ptr())
+        if self.comm.world == 1:
+            self.full[b][0].copy_(self.local[b], non_blocking=True)
+            self.work[b] = None
+        else:
+            self.work[b] = self.comm.dist.all_gather_into_tensor(self.full[b].view(-1, 2), self.local[b], async_op=True)
+
+    def latest(self):
+        b = self.cur
+        if self.work[b] is not None:
+            self.work[b].wait(); self.work[b] = None
+        flat = self.full[b].view(-1, 2).cpu().numpy()
+        out = np.empty_like(flat)
+        out[self.order] = flat
+        return out
+
+    def finish(self):
+        for b in (0, 1):
+            if self.work[b] is not None:
+                self.work[b].wait(); self.work[b] = None
+
+
+def initial_thermo(eng, natoms, mass, st):
+    """thermo record of a freshly uploaded state (what lammps_extract returns after init_sample's last 'run 0'): pe and the
+    pair virial from nm_eval, ke / temp from the velocities, total pressure as compute pressure forms it"""
+    pe, w, _, _ = eng.eval(want_forces=False)
+    ke = 0.5 * mass * (st["v"] ** 2).sum(1)
+    dof = 3.0 * natoms - 3.0
+    temp = 2.0 * ke / dof
+    vol = st["box"] ** 3
+    th = np.zeros((eng.n_rep, nm.THERMO_WIDTH))
+    th[:, 0], th[:, 1], th[:, 2], th[:, 3], th[:, 4], th[:, 5] = temp, pe, ke, (dof * temp + w) / 3.0 / vol, st["box"], vol
+    th[:, 6], th[:, 7], th[:, 8] = st["dx"], st["dv"], st["dt"]
+    return th
 
 
 def run(args, comm=None, log=print):
@@ -304,8 +468,8 @@ def run(args, comm=None, log=print):
     P, T = grids(args.pressure_range[0], args.pressure_range[1], npn, args.temperature_range[0], args.temperature_range[1], ntn)
     dt0 = TIMESTEP[UNITS[el]]
     pref = file_prefix(args.name, el)
-    row0, nrow = comm.row_shard(npn)
-    ns, nloc, off = npn * ntn, nrow * ntn, row0 * ntn
+    rows = comm.row_shard(npn)
+    ns, nloc = npn * ntn, len(rows) * ntn
     natoms = 4 * sz ** 3 if LAT[el][0] == "fcc" else 2 * sz ** 3
     if comm.rank == 0:
         np.save(pref + ".virial.trgt.npy", P)
@@ -313,87 +477,102 @@ def run(args, comm=None, log=print):
     et, pf = init_constants(P, T)
     temp = np.tile(T.astype(np.float64), npn)
     np.random.seed(SEED)
-    rng = np.random.default_rng(SEED)
     device = comm.local_rank if torch.cuda.is_available() else 0
     stream = torch.cuda.current_stream().cuda_stream
-    eng = nm.Engine(natoms=natoms, n_rep=nloc, nt=ntn, n_rep_global=ns, rep_offset=off, device=device,
+    eng = nm.Engine(natoms=natoms, n_rep=nloc, nt=ntn, n_rep_global=ns, rep_offset=comm.rank * ntn, row_stride=comm.world, device=device,
                     nstps=args.timesteps, mod=mod, bulk_move=args.bulk_move, ppos=args.position_move,
                     pvol=args.volume_move, lat_scale=LAT[el][1], mass=MASS[el], rc=RC, seed=SEED, stream=stream)
-    sl = slice(off, off + nloc)
-    eng.set_labels(et[sl], pf[sl], temp[sl])
+    gs = eng.global_slots()                       # global slot k = i*NT + j of every local slot
+    eng.set_labels(et[gs], pf[gs], temp[gs])
     if args.restart:
         rf = os.path.join(os.getcwd(), "%s.%s.%s.lammps.rstrt.%04d.npy" % (args.restart_name, el.lower(), LAT[el][0], args.restart_step))
         _, x, v, box, dx, dv, dt = load_restart(rf)
         box = np.array([text6(b) for b in box])
-        eng.set_state(x=x[sl], v=v[sl], box=box[sl], dx=dx[sl], dv=dv[sl], dt=dt[sl])
-        table = allgather_table(comm, eng, torch)
-        eng.exchange_apply(table.data_ptr(), et, pf, -1, uniforms=np.random.rand(npn * ntn * (ntn - 1) // 2), want_perm=False)
+        eng.set_state(x=x[gs], v=v[gs], box=box[gs], dx=dx[gs], dv=dv[gs], dt=dt[gs])
+        eng.exchange(-1, uniforms=np.random.rand(npn * ntn * (ntn - 1) // 2), want_perm=False)
     else:
-        x, v, box = init_samples(P[row0:row0 + nrow], T, sz, args.pos_displace, np.random.default_rng(SEED + 1 + comm.rank),
-                                 interpolate=args.interpolate_states, device=device)
+        x, v, box = init_samples(P, T, sz, args.pos_displace, SEED, slots=gs, interpolate=args.interpolate_states, device=device)
         box = np.array([text6(b) for b in box])          # init_lammps: 'change_box ... %f'
         eng.set_state(x=x, v=v, box=box, dx=np.full(nloc, args.pos_displace), dv=np.full(nloc, args.vol_displace),
                       dt=np.full(nloc, dt0))
+        if args.interpolate_states:
+            eng.velocity_create(0)                       # the 'velocity create T[j]' draw stays in STATE (:420-425)
     record = cutoff < nsmpl
-    thrm_parts = [[] for _ in range(nloc)]
-    traj_parts = [[] for _ in range(nloc)]
+    writer = None
     if record:
-        for k in range(nloc):
-            i, j = divmod(off + k, ntn)
-            thrm_parts[k].append(header_text(args, P[i], T[j], nsmpl, cutoff, mod, dt0).encode())
+        headers = [header_text(args, P[k // ntn], T[k % ntn], nsmpl, cutoff, mod, dt0).encode() for k in gs.tolist()]
+        if args.direct_npy and comm.world > 1:
+            if comm.rank == 0:
+                StreamWriter(args, pref, [], npn, ntn, natoms, nsmpl - cutoff, [], direct_npy=True, create=True).close()   # creates the memmaps
+            comm.barrier()
+        writer = StreamWriter(args, pref, gs, npn, ntn, natoms, nsmpl - cutoff, headers, nthreads=max(1, args.threads),
+                              direct_npy=args.direct_npy, create=comm.world == 1)
+    gather = TableGather(comm, eng, torch)
+    # STEP = -1: dump_samples_restart() before the loop (lammps_remcmc.py:975-976)
+    st = eng.get_state()
+    _gather_and_dump(comm, pref, 0, natoms, st, initial_thermo(eng, natoms, MASS[el], st), gs, ns)
     swaps_total = 0
     for step in range(nsmpl):
         eng.run_cycle(step)
         th = eng.get_thermo()
         if (step + 1) > cutoff:
             st = eng.get_state(want_v=False)
-            recs = traj_records(natoms, st["box"], st["x"], nthreads=max(1, args.threads))
-            for k in range(nloc):
-                thrm_parts[k].append(thrm_line(th[k]))
-                traj_parts[k].append(recs[k])
+            writer.put(th, st["box"], st["x"])
         eng.adapt()
         if (step + 1) % args.restart_dump == 0:
             st = eng.get_state()
-            _gather_and_dump(comm, torch, pref, step + 1, natoms, st, th, ns, off, nloc)
+            _gather_and_dump(comm, pref, step + 1, natoms, st, th, gs, ns)
         if (step + 1) != nsmpl:
-            table = allgather_table(comm, eng, torch)
-            _, swaps = eng.exchange_apply(table.data_ptr(), et, pf, step)
+            _, swaps = eng.exchange(step)
             swaps_total += swaps
-            if args.verbose and comm.rank == 0:
-                log("%d replica exchanges performed" % swaps)
-    if record:
-        _consolidate(comm, pref, thrm_parts, traj_parts)
+            gather.start()                               # job-wide (pe + ke, vol) table: asynchronous, for the log
+            if args.verbose:
+                tot = _sum_over_ranks(comm, torch, swaps)
+                if comm.rank == 0:
+                    log("%d replica exchanges performed" % tot)
+    gather.finish()
+    if writer is not None:
+        writer.close()
+        comm.barrier()
+        if comm.rank == 0:
+            consolidate_outputs(args, pref, npn, ntn)
     counters = eng.counters()
     eng.close()
-    return counters, swaps_total
+    return counters, _sum_over_ranks(comm, torch, swaps_total)
 
 
-def _gather_and_dump(comm, torch, pref, step, natoms, st, th, ns, off, nloc):
+def _sum_over_ranks(comm, torch, value):
     if comm.world == 1:
-        dump_restart(pref + ".rstrt.%04d.npy" % step, natoms, st, th)
+        return int(value)
+    t = torch.tensor([int(value)], dtype=torch.int64, device="cuda" if torch.cuda.is_available() else "cpu")
+    comm.dist.all_reduce(t)
+    return int(t.item())
+
+
+def _gather_and_dump(comm, pref, step, natoms, st, th, gs, ns):
+    """dump_samples_restart (lammps_remcmc.py:821-828) in global slot order. Multi-rank: every rank writes its part next to the
+    target, rank 0 assembles (the restart file is one object array by format)."""
+    path = pref + ".rstrt.%04d.npy" % step
+    if comm.world == 1:
+        dump_restart(path, natoms, st, th)
         return
-    objs = [None] * comm.world if comm.rank == 0 else None
-    comm.dist.gather_object((st, th), objs, dst=0)
+    part = "%s.part%03d.npz" % (path, comm.rank)
+    np.savez(part, gs=gs, th=th, **st)
+    comm.barrier()
     if comm.rank == 0:
-        full = {k: np.concatenate([o[0][k] for o in objs]) for k in ("x", "v", "box", "dx", "dv", "dt")}
-        dump_restart(pref + ".rstrt.%04d.npy" % step, natoms, full, np.concatenate([o[1] for o in objs]))
-
-
-def _consolidate(comm, pref, thrm_parts, traj_parts):
-    """consolidate_outputs (lammps_remcmc.py:289-316): pressure-major, temperature, sample order"""
-    if comm.world > 1:
-        objs = [None] * comm.world if comm.rank == 0 else None
-        comm.dist.gather_object((thrm_parts, traj_parts), objs, dst=0)
-        if comm.rank != 0:
-            return
-        thrm_parts = [p for o in objs for p in o[0]]
-        traj_parts = [p for o in objs for p in o[1]]
-    with open(pref + ".thrm", "wb") as fh:
-        for parts in thrm_parts:
-            fh.write(b"".join(parts))
-    with open(pref + ".traj", "wb") as fh:
-        for parts in traj_parts:
-            fh.write(b"".join(parts))
+        full = {k: None for k in ("x", "v", "box", "dx", "dv", "dt")}
+        th_full = np.empty((ns, th.shape[1]))
+        for r in range(comm.world):
+            name = "%s.part%03d.npz" % (path, r)
+            with np.load(name) as z:
+                for k in full:
+                    if full[k] is None:
+                        full[k] = np.empty((ns,) + z[k].shape[1:])
+                    full[k][z["gs"]] = z[k]
+                th_full[z["gs"]] = z["th"]
+            os.remove(name)
+        dump_restart(path, natoms, full, th_full)
+    comm.barrier()
 
 
 def main(argv=None):

@@ -265,8 +265,7 @@ def test_exchange_matches_reference_golden(nm, orc, name):
         eng.set_labels(g[name + "_et"], g[name + "_pf"], g[name + "_et"], g[name + "_et"])
         dx0 = g[name + "_dx"]
         eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=dx0, dv=dx0, dt=dx0)
-        perm, swaps = eng.exchange_apply(table.data_ptr(), g[name + "_et"], g[name + "_pf"], 0,
-                                         uniforms=g[name + "_uniforms"])
+        perm, swaps = eng.exchange_apply(table.data_ptr(), 0, uniforms=g[name + "_uniforms"])
         st = eng.get_state()
     np.testing.assert_array_equal(perm, g[name + "_perm"])
     perm_o, swaps_o = orc.exchange(np_, nt, g[name + "_pe"] + g[name + "_ke"], g[name + "_vol"], g[name + "_et"],
@@ -338,10 +337,11 @@ def test_rdf_large_sample_property(nm, orc):
 
 
 # ------------------------------------------------------------------ (e) sharding: N ranks == 1 rank
-def test_row_sharded_engines_reproduce_the_single_engine_run(nm, orc):
-    """two engines holding two pressure rows each (what two ranks hold) give bit-identical thermo, states and swap
-    permutations to one engine holding all four rows: the RNG is keyed on the GLOBAL slot, exchanges are row-local"""
-    import torch
+@pytest.mark.parametrize("layout", ["cyclic", "blocks"])
+def test_row_sharded_engines_reproduce_the_single_engine_run(nm, orc, layout):
+    """two engines holding two pressure rows each (what two ranks hold: rows u mod 2 == rank, or contiguous blocks) give
+    bit-identical thermo, states and swap permutations to one engine holding all four rows: the RNG streams and the exchange
+    draws are keyed on the GLOBAL slot / row, and every engine decides the swaps of its own rows from its own energies"""
     np_, nt, n = 4, 3, 256
     ns = np_ * nt
     x, box = _configs(orc, 4, list(np.linspace(1.1, 0.75, ns)), [0.05] * ns, seed=31)
@@ -351,45 +351,73 @@ def test_row_sharded_engines_reproduce_the_single_engine_run(nm, orc):
     et, pf = T.copy(), P / T
     kw = dict(natoms=n, nt=nt, mod=10, bulk_move=True, seed=77)
 
-    def drive(engines, offs):
-        th_all, perms = [], []
-        for cyc in range(3):
-            for e in engines:
-                e.run_cycle(cyc)
-            th = np.concatenate([e.get_thermo() for e in engines])
-            for e in engines:
-                e.adapt()
-            # the all-gather: every engine packs its slots, the tables are concatenated in rank order
-            parts = []
-            for e in engines:
-                t = torch.empty((e.n_rep, 2), dtype=torch.float64, device="cuda")
-                e.exchange_pack(t.data_ptr())
-                parts.append(t)
-            table = torch.cat(parts)
-            out = [e.exchange_apply(table.data_ptr(), et, pf, cyc) for e in engines]
-            assert all(np.array_equal(out[0][0], o[0]) and out[0][1] == o[1] for o in out)
-            th_all.append(th); perms.append(out[0][0])
-        st = [e.get_state() for e in engines]
-        return np.array(th_all), np.array(perms), {k: np.concatenate([s[k] for s in st]) for k in st[0]}
-
-    def make(n_rep, off):
-        e = nm.Engine(n_rep=n_rep, n_rep_global=ns, rep_offset=off, **kw)
-        sl = slice(off, off + n_rep)
-        e.set_labels(et[sl], pf[sl], T[sl])
-        e.set_state(x=x[sl], v=np.zeros_like(x[sl]), box=box[sl], dx=np.full(n_rep, .03125), dv=np.full(n_rep, .03125),
+    def make(n_rep, off, stride):
+        e = nm.Engine(n_rep=n_rep, n_rep_global=ns, rep_offset=off, row_stride=stride, **kw)
+        gs = e.global_slots()
+        e.set_labels(et[gs], pf[gs], T[gs])
+        e.set_state(x=x[gs], v=np.zeros_like(x[gs]), box=box[gs], dx=np.full(n_rep, .03125), dv=np.full(n_rep, .03125),
                     dt=np.full(n_rep, .00390625))
         return e
 
-    one = [make(ns, 0)]
-    th1, p1, s1 = drive(one, [0])
-    two = [make(ns // 2, 0), make(ns // 2, ns // 2)]
-    th2, p2, s2 = drive(two, [0, ns // 2])
+    def drive(engines):
+        gs = np.concatenate([e.global_slots() for e in engines])
+        th_all, perms, swaps_all = [], [], []
+        for cyc in range(3):
+            for e in engines:
+                e.run_cycle(cyc)
+            th = np.empty((ns, 18))
+            th[gs] = np.concatenate([e.get_thermo() for e in engines])
+            perm, swaps = np.empty(ns, dtype=np.int64), 0
+            for e in engines:
+                e.adapt()
+                p, sw = e.exchange(cyc)
+                perm[e.global_slots()] = e.global_slots()[p]          # local source slot -> global
+                swaps += sw
+            th_all.append(th); perms.append(perm); swaps_all.append(swaps)
+        st = {}
+        for e in engines:
+            for k, v in e.get_state().items():
+                st.setdefault(k, np.empty((ns,) + v.shape[1:]))[e.global_slots()] = v
+        return np.array(th_all), np.array(perms), swaps_all, st
+
+    one = [make(ns, 0, 1)]
+    th1, p1, sw1, s1 = drive(one)
+    two = [make(ns // 2, 0, 2), make(ns // 2, nt, 2)] if layout == "cyclic" else [make(ns // 2, 0, 1), make(ns // 2, ns // 2, 1)]
+    if layout == "cyclic":
+        np.testing.assert_array_equal(two[1].global_slots(), [3, 4, 5, 9, 10, 11])
+    th2, p2, sw2, s2 = drive(two)
     for e in one + two:
         e.close()
+    assert sw1 == sw2
     np.testing.assert_array_equal(p1, p2)
     np.testing.assert_array_equal(th1, th2)
     for k in s1:
         np.testing.assert_array_equal(s1[k], s2[k])
+
+
+def test_exchange_from_a_job_wide_table_on_a_sharded_engine(nm, orc):
+    """nm_exchange_apply on an engine that holds rows 1 and 3 of a 4-row grid: the sweep of each local row reads its
+    entries of the job-wide table and draws the uniforms of its GLOBAL row"""
+    import torch
+    np_, nt, n = 4, 5, 256
+    ns = np_ * nt
+    rng = np.random.default_rng(3)
+    etot, vol = rng.normal(-1500, 30, ns), rng.normal(280, 5, ns)
+    T = np.tile(np.linspace(0.5, 2.0, nt), np_)
+    P = np.repeat(np.linspace(1.0, 6.0, np_), nt)
+    u = orc.exchange_uniforms(256, 7, ns * (nt - 1) // 2)
+    perm_o, _ = orc.exchange(np_, nt, etot, vol, T, P / T, u)
+    table = torch.tensor(np.stack([etot, vol], 1), device="cuda")
+    x, box = _configs(orc, 4, [1.0] * (2 * nt), [0.02] * (2 * nt), seed=9)
+    with nm.Engine(natoms=n, n_rep=2 * nt, nt=nt, n_rep_global=ns, rep_offset=nt, row_stride=2, mod=0, seed=256) as eng:
+        gs = eng.global_slots()
+        eng.set_labels(T[gs], (P / T)[gs], T[gs])
+        eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(2 * nt, .03), dv=np.full(2 * nt, .03), dt=np.full(2 * nt, .004))
+        perm, swaps = eng.exchange_apply(table.data_ptr(), 7)
+        perm_inj, _ = eng.exchange_apply(table.data_ptr(), 7, uniforms=u)
+    np.testing.assert_array_equal(gs[perm], perm_o[gs])
+    np.testing.assert_array_equal(perm, perm_inj)
+    assert swaps > 0 and (perm_o[gs] != gs).any()
 
 
 # ------------------------------------------------------------------ ensemble averages (north star: within 2 sigma)

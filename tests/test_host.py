@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(nm):
     lib = ctypes.CDLL(nm.LIB_PATH)
     for name in sorted(names):
         assert hasattr(lib, name), "libnm_b200.so does not export %s" % name
-    assert lib.nm_abi_version() == 1
+    assert lib.nm_abi_version() == 2
 
 
 def test_no_gpu_is_a_loud_error(nm):
@@ -124,7 +124,8 @@ def test_restart_round_trip(tmp_path):
 
 
 def test_reference_parse_script_consumes_our_files(nm, tmp_path):
-    """acceptance consumer: the UNMODIFIED lammps_parse.py runs on files in our format (build container only)"""
+    """acceptance consumer: the UNMODIFIED lammps_parse.py runs on the files the streaming writer produced (build container
+    only), and the directly emitted .npy files (N2) are bit-identical to what the parser derives from the text"""
     ref = "/root/reference/scripts/lammps_parse.py"
     if not os.path.exists(ref):
         pytest.skip("reference not present (GPU box)")
@@ -139,34 +140,58 @@ def test_reference_parse_script_consumes_our_files(nm, tmp_path):
         pref = remcmc.file_prefix("t", "LJ")
         np.save(pref + ".virial.trgt.npy", P)
         np.save(pref + ".temp.trgt.npy", T)
-        thrm, traj, xs, boxes = [], [], [], []
-        for k in range(pn * tn):
-            i, j = divmod(k, tn)
-            parts = [remcmc.header_text(args, P[i], T[j], s, 0, 128, 0.00390625).encode()]
-            tparts = []
-            for _ in range(s):
-                th = np.abs(rng.normal(size=18)) + 0.1
-                box = rng.uniform(5, 6)
-                x = rng.uniform(0, box, 3 * n)
-                th[4], th[5] = box, box ** 3
-                parts.append(remcmc.thrm_line(th))
-                tparts.append(remcmc.traj_records(n, np.array([box]), x.reshape(1, -1))[0])
-                xs.append(x); boxes.append(box)
-            thrm.append(parts); traj.append(tparts)
-        remcmc._consolidate(remcmc.Comm(), pref, thrm, traj)
+        ns = pn * tn
+        heads = [remcmc.header_text(args, P[k // tn], T[k % tn], s, 0, 128, 0.00390625).encode() for k in range(ns)]
+        w = remcmc.StreamWriter(args, pref, np.arange(ns), pn, tn, n, s, heads, nthreads=3, direct_npy=True)
+        xs, boxes = np.empty((s, ns, 3 * n)), np.empty((s, ns))
+        for q in range(s):
+            th = np.abs(rng.normal(size=(ns, 18))) * 10.0 ** rng.integers(-6, 6, (ns, 18)) + 1e-7
+            boxes[q] = rng.uniform(5, 6, ns)
+            xs[q] = rng.uniform(0, 1, (ns, 3 * n)) * boxes[q][:, None] * 10.0 ** rng.integers(-4, 1, (ns, 3 * n))
+            th[:, 4], th[:, 5] = boxes[q], boxes[q] ** 3
+            w.put(th, boxes[q].copy(), xs[q].copy())
+        w.close()
+        remcmc.consolidate_outputs(args, pref, pn, tn)
+        names = ("pos", "box", "natoms") + remcmc.THERMO_NAMES
+        ours = {name: np.load(pref + ".%s.npy" % name) for name in names}
+        for name in names:
+            os.remove(pref + ".%s.npy" % name)
         subprocess.check_call([sys.executable, ref, "-n", "t"], cwd=str(tmp_path))
-        pos = np.load(pref + ".pos.npy")
-        natoms = np.load(pref + ".natoms.npy")
-        box = np.load(pref + ".box.npy")
-        vol = np.load(pref + ".vol.npy")
+        for name in names:
+            theirs = np.load(pref + ".%s.npy" % name)
+            assert theirs.dtype == ours[name].dtype and theirs.shape == ours[name].shape, name
+            np.testing.assert_array_equal(theirs, ours[name], err_msg=name)
+        pos, natoms, box = ours["pos"], ours["natoms"], ours["box"]
         assert pos.shape == (pn, tn, s, n, 3) and pos.dtype == np.float32
         assert natoms.shape == (pn, tn, s) and natoms.dtype == np.uint16 and (natoms == n).all()
-        assert box.shape == (pn * tn * s,) and vol.shape == (pn, tn, s)
-        want = np.array([[float("%.4E" % v) for v in x] for x in xs], dtype=np.float32).reshape(pn, tn, s, n, 3)
-        np.testing.assert_array_equal(pos, want)
-        np.testing.assert_array_equal(box, np.array([float("%.4E" % b) for b in boxes], dtype=np.float32))
+        assert box.shape == (pn * tn * s,) and ours["vol"].shape == (pn, tn, s)
+        want = np.array([[float("%.4E" % v) for v in row] for row in xs.reshape(-1, 3 * n)], dtype=np.float32).reshape(s, pn, tn, n, 3)
+        np.testing.assert_array_equal(pos, want.transpose(1, 2, 0, 3, 4))
     finally:
         os.chdir(cwd)
+
+
+def test_streaming_writer_text_equals_the_one_shot_formatter(nm, tmp_path):
+    """the appended per-replica records are byte-identical to format_thrm / format_traj (golden-pinned above); runs on the GPU box too"""
+    from neuralmelting_b200 import remcmc
+    rng = np.random.default_rng(4)
+    ns, n = 5, 7
+    box = rng.uniform(5, 9, ns)
+    x = rng.normal(0, 3, (ns, 3 * n))
+    vals = rng.normal(0, 1, (ns, 17)) * 10.0 ** rng.integers(-9, 9, (ns, 17))
+    paths = [str(tmp_path / ("r%d.traj" % k)) for k in range(ns)]
+    tpaths = [str(tmp_path / ("r%d.thrm" % k)) for k in range(ns)]
+    for rep in range(2):
+        pos, bx = nm.append_traj_batch(n, box, x, paths, nthreads=2, parse_back=True)
+        parsed = nm.append_thrm_batch(vals, tpaths, parse_back=True)
+    for k in range(ns):
+        assert open(paths[k], "rb").read() == 2 * nm.format_traj(n, box[k], x[k])
+        assert open(tpaths[k], "rb").read() == 2 * nm.format_thrm(vals[k])
+    np.testing.assert_array_equal(pos.reshape(ns, -1), np.array([[np.float32(float("%.4E" % v)) for v in row] for row in x]))
+    np.testing.assert_array_equal(bx, np.array([np.float32(float("%.4E" % b)) for b in box]))
+    np.testing.assert_array_equal(parsed, np.array([[np.float32(float("%.4E" % v)) for v in row] for row in vals]))
+    with pytest.raises(nm.NmError):
+        nm.append_traj_batch(n, box, x, [str(tmp_path / "no_such_dir" / "a.traj")] * ns)
 
 
 def test_distr_setup_matches_reference_golden():

@@ -49,7 +49,7 @@ def main():
             cyc, dt * 1e3, ct["hmc_atom_steps"] / dt, ct["sweeps"] / dt, flops / dt / 1e12, ct["list_builds"], ct["force_evals"],
             ct["list_pairs"] / max(1, ct["pairs_force"] + ct["pairs_full"]), sw, th[:, 17].mean(), th[:, 16].mean(), th[:, 15].mean()))
         print("   per-call clk: outer %.0f inner %.0f vel %.0f | share outer %.2f inner %.2f vel %.2f" % (ct["clk_outer"] / max(1, ct["outer_builds"] or ct["list_builds"]), ct["clk_inner"] / max(1, ct["list_builds"]), ct["clk_vel"] / max(1, ct["hmc_moves"]), ct["clk_outer"] / ct["clk_total"], ct["clk_inner"] / ct["clk_total"], ct["clk_vel"] / ct["clk_total"]))
-        print("   thread0 pair loop: %.0f clk per quad-iteration, %.1f quads/eval, loop %.0f clk/eval" % (ct["dbg_loopclk"] / max(1, ct["dbg_loopit"]), ct["dbg_loopit"] / max(1, ct["force_evals"]), ct["dbg_loopclk"] / max(1, ct["force_evals"])))
+        print("   build phases (debug build): tiles %.0f  tiles+ghost table %.0f  row walk %.0f  clk per build" % (ct["clk_outer"] / max(1, ct["list_builds"]), ct["dbg_loopit"] / max(1, ct["list_builds"]), ct["dbg_loopclk"] / max(1, ct["list_builds"])))
         print("   outer builds %d | clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["outer_builds"], ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
     clk = eng.cta_clocks().astype(float).reshape(np_, nt) / 1e6
     print("per-slot Mclk by temperature (mean over P):", np.round(clk.mean(0), 1))
@@ -61,6 +61,18 @@ def main():
         r = rc[k]
         print("%4d  %.2f  %.3f  %5.1f  %4d %4d  %4d  %5d   %6.1f  %6.1f   %7.0f" % (k, tt[k], n / th[k, 5], r[ci["clk_total"]] / 1e6, r[ci["sweeps"]], r[ci["hmc_moves"]],
               r[ci["list_builds"]], r[ci["force_evals"]], r[ci["clk_build"]] / 1e6, r[ci["clk_eval"]] / 1e6, r[ci["list_pairs"]] / max(1, r[ci["force_evals"]])))
+    if os.environ.get("SMID"):
+        smid = rc[:, ci["reserved"]].astype(int)
+        cnt = np.bincount(smid, minlength=160)
+        print("CTAs per SM histogram:", np.bincount(cnt[:int(smid.max()) + 1]), " distinct SMs:", (cnt > 0).sum(), " max smid:", smid.max())
+        clkm = rc[:, ci["clk_total"]] / 1e6
+        for nshare in (1, 2):
+            sel = cnt[smid] == nshare
+            if sel.any():
+                print("  CTAs on SMs with %d CTA(s): n=%d mean Mclk %.1f max %.1f" % (nshare, sel.sum(), clkm[sel].mean(), clkm[sel].max()))
+        pair_sum = np.zeros(160)
+        np.add.at(pair_sum, smid, clkm)
+        print("  per-SM sum of CTA Mclk: min %.1f mean %.1f max %.1f" % (pair_sum[cnt > 0].min(), pair_sum[cnt > 0].mean(), pair_sum[cnt > 0].max()))
     ctot = np.sort(rc[:, ci["clk_total"]] / 1e6)[::-1]
     print("sorted clk_total (Mclk) deciles:", np.round(ctot[::max(1, len(ctot) // 16)], 1), " kernel %.1f Mclk at 1.965 GHz; sum/148 = %.1f" % (dt * 1965e6 / 1e6, ctot.sum() / 148))
     print("T col0 thermo:", np.round(th[:nt, :6], 3)[::max(1, nt // 4)])
