@@ -451,7 +451,7 @@ def run_rdf(args, comm=None, steps=None, nsamples=None):
     comm = comm or remcmc.Comm()
     dev = comm.local_rank
     torch.cuda.set_device(dev)
-    steps = steps or steps
+    steps = steps or args.steps
     n, sb, ns = 4000, 64, nsamples or args.rdf_samples
     rng = np.random.default_rng(5 + comm.rank)
     box = rng.uniform(15.2, 20.5, ns).astype(np.float32)                 # the density range of the 32x32 grid

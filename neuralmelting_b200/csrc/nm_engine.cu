@@ -1320,109 +1320,292 @@ __device__ void hamiltonian_mc(const Dev& d, Ctx& cx, const Rng& r, double et, d
   if (acc) { en.pe = o[0]; en.w = o[1]; cx.in_move = 0; } else restore_xf(d, cx, true);
 }
 
+// clock read that the compiler cannot move across barriers or memory operations (debug timing)
+__device__ __forceinline__ long long clk_fenced() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
+
+// Step (C) of iter_position_mc (see there): ordered commit of a window of speculative single-atom trials by ONE warp,
+// lane l holding trial k + l. Everything that does not depend on the acceptances is done for all lanes at once, before
+// and after the serial loop, which is left with: broadcast the running dE of trial t, compare it with the trial's
+// threshold band, and on acceptance add c(t, l) to the later lanes.
+//  before: the window is cut at the first trial that was not evaluated or whose list column is not guaranteed complete
+//          if EVERY earlier trial of the window is accepted (prefix maximum of the displacements: a bound of the
+//          running maximum at its turn, so the test is conservative; trial 0 was tested against the exact value);
+//  after : the accepted lanes move their atoms (all at once), the displacement maxima take the accepted trials in.
+// win: window records (WS doubles per trial, see WS_*); corr: c(a, b) at [a * CS + b]; res: out {next k, need rebuild};
+// resd: in/out {umax, umaxo}, accumulators {trials, accepted, visited}.
+constexpr int WS = 12;
+enum { WS_XN = 0, WS_YN, WS_ZN, WS_DE, WS_LO, WS_HI, WS_UACC, WS_UN, WS_UNO, WS_FLAG_VIS, WS_SRC };
+// the reference's rule (lammps_remcmc.py:532-547) for a dE inside the threshold band (or not finite, or so negative
+// that exp(-dE/et) could overflow: inf => reject without drawing)
+__device__ __noinline__ bool decide_exact(double de, double et, double uacc) {
+  const double m = exp(-(de / et));
+  return !(isinf(m) || isnan(m)) && uacc <= (m < 1.0 ? m : 1.0);
+}
+__device__ __noinline__ void commit_window(const double* win, const double* corr, double* sp, const uint32_t* ginfo, int ghost, int Npad,
+                                           int CS, int nwin, int k, double L, double s, double so, double rl, double rlo, double rcg,
+                                           double et, int* res, double* resd) {
+  const int lane = threadIdx.x & 31;
+  const bool mine = lane < nwin;
+  const double* wl = win + WS * (mine ? lane : 0);
+  double de = wl[WS_DE];                                 // running dE of trial k + lane
+  const double un = mine ? wl[WS_UN] : 0.0, uno = mine ? wl[WS_UNO] : 0.0;
+  const int flag = mine ? reinterpret_cast<const int*>(wl + WS_FLAG_VIS)[0] : 3, src = reinterpret_cast<const int*>(wl + WS_SRC)[0];
+  const double um = resd[0], umo = resd[1];
+  // ---- before: how far the window can be committed
+  double pm = un, pmo = uno;                             // exclusive prefix maxima of the displacements (with the maxima so far)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double a = __shfl_up_sync(0xffffffffu, pm, o), b = __shfl_up_sync(0xffffffffu, pmo, o);
+    if (lane >= o) { pm = fmax(pm, a); pmo = fmax(pmo, b); }
+  }
+  pm = __shfl_up_sync(0xffffffffu, pm, 1); pmo = __shfl_up_sync(0xffffffffu, pmo, 1);
+  pm = lane ? fmax(pm, um) : um; pmo = lane ? fmax(pmo, umo) : umo;
+  const bool ok = lane == 0 || (src == 0 ? (s * (rl - un - pm) >= rcg && s * (rl - 2.0 * pm) >= rcg)
+                                         : (so * (rlo - uno - pmo) >= rcg && so * (rlo - 2.0 * pmo) >= rcg));
+  const unsigned stop = __ballot_sync(0xffffffffu, flag != 0 || !ok);
+  const int tmax = stop ? __ffs(stop) - 1 : 32;          // <= nwin: lanes past the window carry flag 3
+  const int need = tmax == 0 && __shfl_sync(0xffffffffu, flag, 0) == 1;
+  // ---- the serial chain
+  const double floor_ = -600.0 * et;
+  unsigned accmask = 0u;
+  for (int t = 0; t < tmax; t++) {
+    const double* wt = win + WS * t;
+    const double de_t = __shfl_sync(0xffffffffu, de, t);
+    const double lo = wt[WS_LO], hi = wt[WS_HI], c_t = corr[t * CS + lane];
+    bool acc;
+    if (de_t > floor_ && de_t < lo) acc = true;
+    else if (de_t > hi) acc = false;
+    else acc = decide_exact(de_t, et, wt[WS_UACC]);
+    if (acc) { accmask |= 1u << t; if (lane > t) de += c_t; }
+  }
+  // ---- after: move the accepted atoms (store_pos on the values passed in), update the maxima and the counters
+  const bool moved = (accmask >> lane) & 1u;
+  if (moved) {
+    const int i = k + lane;
+    const double x = wl[WS_XN], y = wl[WS_YN], z = wl[WS_ZN];
+    sp[3 * i] = x; sp[3 * i + 1] = y; sp[3 * i + 2] = z;
+    if (ghost) {
+      const uint32_t gi = ginfo[i];
+      const unsigned nb = gi & 7u;
+      if (nb) {
+        const double xs = x + ((gi & 8u) ? L : -L), ys = y + ((gi & 16u) ? L : -L), zs = z + ((gi & 32u) ? L : -L);
+        double* q = sp + 3 * (size_t)(Npad + (gi >> 8));
+        for (unsigned g = 1; g < 8; g++)
+          if ((g & ~nb) == 0u) { q[0] = (g & 1u) ? xs : x; q[1] = (g & 2u) ? ys : y; q[2] = (g & 4u) ? zs : z; q += 3; }
+      }
+    }
+  }
+  double mx = moved ? un : 0.0, mxo = moved ? uno : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mxo = fmax(mxo, __shfl_xor_sync(0xffffffffu, mxo, o)); }
+  int v = lane < tmax ? reinterpret_cast<const int*>(wl + WS_FLAG_VIS)[1] : 0;
+  v = __reduce_add_sync(0xffffffffu, v);
+  if (lane == 0) {
+    res[0] = k + tmax; res[1] = need;
+    resd[0] = fmax(um, mx); resd[1] = fmax(umo, mxo); resd[2] += (double)tmax; resd[3] += (double)__popc(accmask); resd[4] += (double)v;
+  }
+}
+
 // ------------------------------------------------------------------ a-8 iter_position_mc (lammps_remcmc.py:505-549)
-// The reference re-evaluates the whole system for each of the N sequential single-atom trials; here warp 0
-// walks the same sequential chain with the single-atom energy change summed over the atom's list column.
+// The reference re-evaluates the whole system for each of the N sequential single-atom trials; here the same sequential
+// chain is walked with the single-atom energy change summed over the atom's list column, a WINDOW of W trials (one per
+// warp) at a time, in three steps:
+//  (A) every warp w draws the proposal of trial k + w (position, acceptance uniform, displacement from the list
+//      references) and publishes it;
+//  (B) every warp evaluates its trial SPECULATIVELY against the configuration at the start of the round (dE over the
+//      list column: the lanes split the quads), and lane a < w evaluates the CORRECTION trial w would need if the
+//      earlier trial a of the window were accepted -- the four pair terms that involve atom a,
+//          c(a, w) = [u(w_new, a_new) - u(w_old, a_new)] - [u(w_new, a_old) - u(w_old, a_old)]
+//      (a's proposal is known from step A whether or not it will be accepted);
+//  (C) warp 0 commits the window IN ORDER, lane l holding trial k + l: at turn t the running dE of trial t (its
+//      speculative dE plus the corrections of the accepted trials before it, added in window order) is broadcast and
+//      decided; if accepted, atom k + t moves and every later lane adds its c(t, l). A rejected trial changes nothing.
+//      This is the reference's chain term by term (each trial sees exactly the positions its predecessors left); only
+//      the order of the floating-point additions differs from a fresh sum. The serial part is ~100 clocks per trial.
+// The Metropolis test U <= min(1, exp(-dE/et)) is decided by comparing dE with the threshold -et ln U prepared in
+// step A; the exponential itself is evaluated only when dE lies within 1e-9 of the threshold (or could overflow), so
+// the decisions are those of the exact rule.
+// Which column is complete for a trial: the inner list (radius rc + skin) while the trial's and the largest
+// displacement since its build fit the skin; otherwise (LARGE mode) the OUTER list column (radius rc + skin + outer
+// skin, three times as many entries) -- a single-atom sweep at the adapted step size would otherwise rebuild the
+// inner list dozens of times. A window ends early at a trial whose column is not guaranteed complete for the
+// displacement budget at ITS turn (re-checked at commit time with the running maxima); that trial opens the next
+// round, where the first trial may also take the slow paths (list rebuild, or an all-atom sum when the step exceeds
+// the skin). Deterministic: the schedule depends on the chain state only.
+// Scratch: the window records live in the reduction scratch, the W x W correction table in the float32 fractional
+// copies (cx.sf), which only list builds and the FP32 force loop read -- both refresh them first.
 template <bool S32>
 __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et, double dxs, Energy& en, double* cnt) {
-  const int N = cx.N, Npad = cx.Npad, lane = threadIdx.x & 31;
-  const double rc = d.rc, rc2 = rc * rc, rl = rc + d.skin, L = cx.L, hL = 0.5 * L, invL = 1.0 / L;
+  const int N = cx.N, Npad = cx.Npad, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int nw = blockDim.x >> 5;              // window: one trial per warp, as long as the correction table fits its scratch
+  while (nw > 1 && nw * (nw + 1) > 2 * Npad) nw--;
+  const int CS = nw + 1;                 // row stride of the correction table (odd: conflict-free): c(a, b) at corr[a * CS + b]
+  const double rc = d.rc, rc2 = rc * rc, rl = rc + d.skin, rlo = rl + d.oskin, L = cx.L, hL = 0.5 * L, invL = 1.0 / L;
+  const double rcg = rc * (1 + 1e-9);
+  const int L_hi = __double2hiint(L), L_lo = __double2loint(L), hL_hi = __double2hiint(hL);
+  const bool two_level = !d.small;
   check_list(d, cx);
-  // umax: largest displacement (build units) of any atom from its list reference
-  double um[1] = { 0.0 };
-  {
-    double mx = 0.0;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmax(mx, disp2(cx, i, cx.sp[3 * (i)], cx.sp[3 * (i) + 1], cx.sp[3 * (i) + 2], invL));
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  // um / umo: largest displacement (build units) of any atom from its inner / outer list reference
+  double um = 0.0, umo = 0.0;
+  auto max_displacements = [&]() {
+    double mx = 0.0, mxo = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const double x = cx.sp[3 * i], y = cx.sp[3 * i + 1], z = cx.sp[3 * i + 2];
+      mx = fmax(mx, disp2(cx, i, x, y, z, invL));
+      if (two_level) mxo = fmax(mxo, disp2o(cx, i, x, y, z, invL));
+    }
+    for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); mxo = fmax(mxo, __shfl_xor_sync(0xffffffffu, mxo, o)); }
     __syncthreads();
-    if (lane == 0) cx.red[threadIdx.x >> 5] = mx;
+    if (lane == 0) { cx.red[wid] = mx; cx.red[32 + wid] = mxo; }
     __syncthreads();
-    if (threadIdx.x == 0) { double q = 0.0; for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) q = fmax(q, cx.red[w]); cx.bc[8] = sqrt(q); }
+    if (threadIdx.x == 0) {
+      double q = 0.0, qo = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) { q = fmax(q, cx.red[w]); qo = fmax(qo, cx.red[32 + w]); }
+      cx.bc[8] = sqrt(q); cx.bc[9] = sqrt(qo);        // bc[8..12]: umax, umaxo, and the sweep's trials / accepted / visited (commit_window)
+    }
     __syncthreads();
-    um[0] = cx.bc[8];
-  }
+    um = cx.bc[8]; umo = cx.bc[9];
+    __syncthreads();
+  };
+  max_displacements();
+  // LARGE mode: start the sweep from a fresh inner list unless the current one is all but fresh. A trial may use its inner
+  // column while un + um <= skin; with the budget already half spent by earlier moves most trials of the sweep would fall
+  // back to the outer column (three passes of the warp instead of one): a rebuild costs ~20 rounds of a 125-round sweep.
+  if (two_level && um > 0.05 * d.skin) { build_list(d, cx); max_displacements(); }
+  if (threadIdx.x == 0) { cx.bc[10] = 0.0; cx.bc[11] = 0.0; cx.bc[12] = 0.0; }
+  double* win = cx.red;
+  double* corr = reinterpret_cast<double*>(cx.sf);
+  static_assert(32 * WS <= RED_DOUBLES, "window scratch");
+  // pair energy with the cutoff from a separation (minimum image on the integer pipe)
+  auto u_lj = [&](double ax, double ay, double az) -> double {
+    ax = mic_fast(ax, L_hi, L_lo, hL_hi); ay = mic_fast(ay, L_hi, L_lo, hL_hi); az = mic_fast(az, L_hi, L_lo, hL_hi);
+    const double rr = ax * ax + ay * ay + az * az, i2 = rcp_nr(rr), s6 = i2 * i2 * i2;
+    return rr < rc2 ? s6 * (4.0 * s6 - 4.0) : 0.0;
+  };
   int k = 0;
-  unsigned long long ntrial = 0, nacc = 0, nvis = 0;
   while (k < N) {
-    if (threadIdx.x < 32) {
-      double umax = um[0];
-      const double s = L / cx.L0;
-      int kk = k, need = 0;
-      // software pipeline: the list column, quad count and list reference of the NEXT atom are fetched from global
-      // memory while the current trial is evaluated (one warp walks the sequential chain; latency is everything)
-      int nq_n = cx.nnb[kk];
-      ushort4 e4_n = lane < nq_n ? cx.list[(size_t)lane * Npad + kk] : make_ushort4(0, 0, 0, 0);
-      double x0_n = lane < 3 ? cx.gx0[lane * Npad + kk] : 0.0;
-      for (; kk < N; kk++) {
-        const int nq = nq_n; const ushort4 e4c = e4_n; const double x0c = x0_n;
-        if (kk + 1 < N) {
-          nq_n = cx.nnb[kk + 1];
-          e4_n = lane < nq_n ? cx.list[(size_t)lane * Npad + kk + 1] : make_ushort4(0, 0, 0, 0);
-          x0_n = lane < 3 ? cx.gx0[lane * Npad + kk + 1] : 0.0;
-        }
-        double u[3]; rng_uniform3(r, (uint32_t)kk, P_ITER_DISP, u);
-        const double uacc = rng_uniform(r, (uint32_t)kk, P_ITER_ACC);       // independent of the energy: off the critical path
-        const double xo = cx.sp[3 * kk], yo = cx.sp[3 * kk + 1], zo = cx.sp[3 * kk + 2];
-        double xn = xo + 2 * (u[0] - 0.5) * dxs * d.lat, yn = yo + 2 * (u[1] - 0.5) * dxs * d.lat, zn = zo + 2 * (u[2] - 0.5) * dxs * d.lat;
-        double un;
-        {
-          const double rx = __shfl_sync(0xffffffffu, x0c, 0), ry = __shfl_sync(0xffffffffu, x0c, 1), rz = __shfl_sync(0xffffffffu, x0c, 2);
-          double ux = xn * invL - rx, uy = yn * invL - ry, uz = zn * invL - rz;
-          ux -= rint(ux); uy -= rint(uy); uz -= rint(uz);
-          un = sqrt(ux * ux + uy * uy + uz * uz) * cx.L0;
-        }
-        // every atom within rc of the old or the new position must be in column kk of the list
-        const bool list_ok = s * (rl - un - umax) >= rc * (1 + 1e-9) && s * (rl - 2.0 * umax) >= rc * (1 + 1e-9);
-        bool brute = false;
-        if (!list_ok) {
+    const double s = L / cx.L0, so = two_level ? L / cx.L0o : 1.0;
+    const int kk = k + wid, nwin = min(nw, N - k);
+#ifdef NM_DEBUG_CLOCKS
+    const long long t_round0 = clk_fenced();
+#endif
+    // ---- (A) proposal of trial kk
+    int nq = 0, flag = 3, src = 0;
+    ushort4 e4c = make_ushort4(0, 0, 0, 0);
+    double xo = 0, yo = 0, zo = 0, xn = 0, yn = 0, zn = 0;
+    if (wid < nwin) {
+      nq = cx.nnb[kk];
+      e4c = lane < nq ? cx.list[(size_t)lane * Npad + kk] : make_ushort4(0, 0, 0, 0);
+      double x0c = lane < 3 ? cx.gx0[lane * Npad + kk] : 0.0;
+      if (two_level && lane >= 3 && lane < 6) x0c = cx.gx0o[(lane - 3) * Npad + kk];
+      // the trial's three Philox blocks (two for the displacement, one for the acceptance uniform) in ONE pass: lanes 0, 1, 2
+      // take one counter each, the words are broadcast (same streams as rng_uniform3 / rng_uniform)
+      double u[3], uacc;
+      {
+        const uint32_t c0 = lane == 2 ? (uint32_t)kk : 2u * (uint32_t)kk + (lane == 1 ? 1u : 0u), c1 = lane == 2 ? (uint32_t)P_ITER_ACC : (uint32_t)P_ITER_DISP;
+        uint32_t w[4]; philox4x32_10(r.k0, r.k1, c0, c1, r.m_lo, r.m_hi, w);
+        const double ua = u53(w[0], w[1]), ub = u53(w[2], w[3]);
+        u[0] = __shfl_sync(0xffffffffu, ua, 0); u[1] = __shfl_sync(0xffffffffu, ub, 0); u[2] = __shfl_sync(0xffffffffu, ua, 1);
+        uacc = __shfl_sync(0xffffffffu, ua, 2);
+      }
+      // accept <=> dE <= thr = -et ln U up to rounding: decided by comparison outside the band thr -+ 2e-9 |thr|, by the exact rule inside
+      const double thr = -log(uacc) * et, band = 2e-9 * fabs(thr) + 1e-290;
+      xo = cx.sp[3 * kk]; yo = cx.sp[3 * kk + 1]; zo = cx.sp[3 * kk + 2];
+      xn = xo + 2 * (u[0] - 0.5) * dxs * d.lat; yn = yo + 2 * (u[1] - 0.5) * dxs * d.lat; zn = zo + 2 * (u[2] - 0.5) * dxs * d.lat;
+      double un, uno = 0.0;
+      {
+        const double rx = __shfl_sync(0xffffffffu, x0c, 0), ry = __shfl_sync(0xffffffffu, x0c, 1), rz = __shfl_sync(0xffffffffu, x0c, 2);
+        double ux = xn * invL - rx, uy = yn * invL - ry, uz = zn * invL - rz;
+        ux -= rint(ux); uy -= rint(uy); uz -= rint(uz);
+        un = sqrt(ux * ux + uy * uy + uz * uz) * cx.L0;
+      }
+      if (two_level) {
+        const double rx = __shfl_sync(0xffffffffu, x0c, 3), ry = __shfl_sync(0xffffffffu, x0c, 4), rz = __shfl_sync(0xffffffffu, x0c, 5);
+        double ux = xn * invL - rx, uy = yn * invL - ry, uz = zn * invL - rz;
+        ux -= rint(ux); uy -= rint(uy); uz -= rint(uz);
+        uno = sqrt(ux * ux + uy * uy + uz * uz) * cx.L0o;
+      }
+      // every atom within rc of the old or the new position must be in the column that is summed
+      const bool inner_ok = s * (rl - un - um) >= rcg && s * (rl - 2.0 * um) >= rcg;
+      const bool outer_ok = two_level && cx.thro2 >= 0.0 && so * (rlo - uno - umo) >= rcg && so * (rlo - 2.0 * umo) >= rcg;
+      flag = 0;                          // 0: evaluated, 1: a fresh list would do (rebuild, then retry), 3: not evaluated (opens a later round)
+      src = inner_ok ? 0 : (outer_ok ? 1 : 2);          // column summed: inner list, outer list, all atoms
+      if (src == 2) {
+        if (wid == 0) {
           const double ddx = mic_exact(xn - xo, L, hL), ddy = mic_exact(yn - yo, L, hL), ddz = mic_exact(zn - zo, L, hL);
           const double step = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
-          if (rl - step >= rc * (1 + 1e-9)) { need = 1; break; }   // a fresh list would do: rebuild, then retry kk
-          brute = true;                                            // step larger than the skin: all-atom sum
+          if (rl - step >= rcg) flag = 1;               // else: step larger than the skin, all-atom sum
+        } else flag = 3;
+      }
+      if (lane == 0) {
+        double* t = win + WS * wid;
+        t[WS_XN] = xn; t[WS_YN] = yn; t[WS_ZN] = zn; t[WS_LO] = thr - band; t[WS_HI] = thr + band; t[WS_UACC] = uacc; t[WS_UN] = un; t[WS_UNO] = uno;
+        reinterpret_cast<int*>(t + WS_FLAG_VIS)[0] = flag; reinterpret_cast<int*>(t + WS_SRC)[0] = src;
+      }
+    }
+    __syncthreads();
+#ifdef NM_DEBUG_CLOCKS
+    if (threadIdx.x == 0) cx.ct[NM_CT_CLK_VEL] += (unsigned long long)(clk_fenced() - t_round0);
+#endif
+    // ---- (B) speculative dE of trial kk, and its corrections for the earlier trials of the window
+    if (wid < nwin && flag == 0) {
+      double de = 0.0; int vis = 0;
+      auto pair = [&](int j) {
+        const double ax = mic_exact(xn - cx.sp[3 * j], L, hL), ay = mic_exact(yn - cx.sp[3 * j + 1], L, hL), az = mic_exact(zn - cx.sp[3 * j + 2], L, hL);
+        const double bx = mic_exact(xo - cx.sp[3 * j], L, hL), by = mic_exact(yo - cx.sp[3 * j + 1], L, hL), bz = mic_exact(zo - cx.sp[3 * j + 2], L, hL);
+        const double rn = ax * ax + ay * ay + az * az, ro = bx * bx + by * by + bz * bz;
+        const double r2n = rcp_nr(rn), r2o = rcp_nr(ro);
+        const double r6n = r2n * r2n * r2n, r6o = r2o * r2o * r2o;
+        if (rn < rc2) { de += r6n * (4.0 * r6n - 4.0); vis++; }
+        if (ro < rc2) { de -= r6o * (4.0 * r6o - 4.0); vis++; }
+      };
+      if (src == 2) {
+        for (int j = lane; j < N; j += 32) if (j != kk) pair(j);
+      } else if (src == 1) {
+        const int nqo = cx.onq[kk];
+        for (int q = lane; q < nqo; q += 32) {
+          const ushort4 e4 = cx.olist[(size_t)q * Npad + kk];
+          pair(e4.x); pair(e4.y); pair(e4.z); pair(e4.w);
         }
-        double de = 0.0; int vis = 0;
-        auto pair = [&](int j) {
-          const double ax = mic_exact(xn - cx.sp[3 * j], L, hL), ay = mic_exact(yn - cx.sp[3 * j + 1], L, hL), az = mic_exact(zn - cx.sp[3 * j + 2], L, hL);
-          const double bx = mic_exact(xo - cx.sp[3 * j], L, hL), by = mic_exact(yo - cx.sp[3 * j + 1], L, hL), bz = mic_exact(zo - cx.sp[3 * j + 2], L, hL);
-          const double rn = ax * ax + ay * ay + az * az, ro = bx * bx + by * by + bz * bz;
-          const double r2n = rcp_nr(rn), r2o = rcp_nr(ro);
-          const double r6n = r2n * r2n * r2n, r6o = r2o * r2o * r2o;
-          if (rn < rc2) { de += r6n * (4.0 * r6n - 4.0); vis++; }
-          if (ro < rc2) { de -= r6o * (4.0 * r6o - 4.0); vis++; }
-        };
-        if (brute) {
-          for (int j = lane; j < N; j += 32) if (j != kk) pair(j);
-        } else {
-          if (lane < nq) { pair(e4c.x & 0x1fff); pair(e4c.y & 0x1fff); pair(e4c.z); pair(e4c.w); }
-          for (int q = lane + 32; q < nq; q += 32) {
-            const ushort4 e4 = cx.list[(size_t)q * Npad + kk];
-            pair(e4.x & 0x1fff); pair(e4.y & 0x1fff); pair(e4.z); pair(e4.w);
-          }
-        }
-        for (int o = 16; o > 0; o >>= 1) { de += __shfl_xor_sync(0xffffffffu, de, o); vis += __shfl_xor_sync(0xffffffffu, vis, o); }
-        bool acc;
-        { const double m = exp(-(de / et)); acc = !(isinf(m) || isnan(m)) && uacc <= (m < 1.0 ? m : 1.0); }
-        ntrial++; nvis += vis;
-        if (acc) {
-          nacc++; en.pe += de;
-          __syncwarp();
-          if (lane == 0) store_pos(cx, kk, xn, yn, zn);
-          __syncwarp();
-          umax = fmax(umax, un);
+      } else {
+        if (lane < nq) { pair(e4c.x & 0x1fff); pair(e4c.y & 0x1fff); pair(e4c.z); pair(e4c.w); }
+        for (int q = lane + 32; q < nq; q += 32) {
+          const ushort4 e4 = cx.list[(size_t)q * Npad + kk];
+          pair(e4.x & 0x1fff); pair(e4.y & 0x1fff); pair(e4.z); pair(e4.w);
         }
       }
-      if (lane == 0) { cx.ibc[1] = kk; cx.ibc[2] = need; cx.bc[8] = umax; }
+      if (lane < wid) {                  // c(a = lane, b = wid)
+        const double* ta = win + WS * lane;
+        const double anx = ta[WS_XN], any_ = ta[WS_YN], anz = ta[WS_ZN];
+        const double aox = cx.sp[3 * (k + lane)], aoy = cx.sp[3 * (k + lane) + 1], aoz = cx.sp[3 * (k + lane) + 2];
+        corr[lane * CS + wid] = (u_lj(xn - anx, yn - any_, zn - anz) - u_lj(xo - anx, yo - any_, zo - anz))
+                              - (u_lj(xn - aox, yn - aoy, zn - aoz) - u_lj(xo - aox, yo - aoy, zo - aoz));
+      }
+      for (int o = 16; o > 0; o >>= 1) { de += __shfl_xor_sync(0xffffffffu, de, o); vis += __shfl_xor_sync(0xffffffffu, vis, o); }
+      if (lane == 0) { win[WS * wid + WS_DE] = de; reinterpret_cast<int*>(win + WS * wid + WS_FLAG_VIS)[1] = vis; }
+    }
+    __syncthreads();
+#ifdef NM_DEBUG_CLOCKS
+    const long long t_round1 = clk_fenced();
+    if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(t_round1 - t_round0); cx.ct[NM_CT_RESERVED]++; }
+#endif
+    // ---- (C) ordered commit: lane l holds the running dE of trial k + l
+    if (wid == 0) {
+      __syncwarp();                      // the warp enters the serial chain converged (a diverged warp pays a re-synchronisation per shuffle)
+      commit_window(win, corr, cx.sp, cx.ginfo, cx.ghost, Npad, CS, nwin, k, L, s, so, rl, rlo, rcg, et, cx.ibc + 1, cx.bc + 8);
+#ifdef NM_DEBUG_CLOCKS
+      if (lane == 0) cx.ct[NM_CT_DBG_LOOPIT] += (unsigned long long)(clk_fenced() - t_round1);
+#endif
     }
     __syncthreads();
     k = cx.ibc[1];
     const int need = cx.ibc[2];
-    um[0] = cx.bc[8];
-    __syncthreads();
-    if (need) { build_list(d, cx); um[0] = 0.0; }
+    um = cx.bc[8]; umo = cx.bc[9];
+    if (need) { __syncthreads(); build_list(d, cx); max_displacements(); }   // (the build's reductions use the window scratch)
   }
   if (threadIdx.x == 0) {
-    cnt[0] += (double)ntrial; cnt[1] += (double)nacc;
-    cx.ct[NM_CT_PMC_MOVES]++; cx.ct[NM_CT_PMC_TRIALS] += ntrial; cx.ct[NM_CT_PAIRS_DELTA] += nvis;
+    cnt[0] += cx.bc[10]; cnt[1] += cx.bc[11];
+    cx.ct[NM_CT_PMC_MOVES]++; cx.ct[NM_CT_PMC_TRIALS] += (unsigned long long)cx.bc[10]; cx.ct[NM_CT_PAIRS_DELTA] += (unsigned long long)cx.bc[12];
   }
   // the state the last 'run 0' of the sweep leaves: a fresh full evaluation
   check_list(d, cx);
@@ -1893,7 +2076,10 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   d.ppos = cfg->ppos; d.pvol = cfg->pvol; d.lat = cfg->lat_scale; d.mass = cfg->mass; d.rc = cfg->rc;
   // default skin: tuned at the stationary state of the default workload (step sizes adapted to 50 % acceptance, 1.6
   // rebuilds per move): 0.4 where a rebuild costs 3 evaluations (hit-matrix builds), 0.3 with the cheaper two-level lists
-  d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : 0.3);
+  // Iterative single-atom sweeps at N > 768 (bulk_move = 0): 0.5, so that a trial's displacement plus the largest one of the
+  // sweep so far (both up to sqrt(3) dx lat ~ 0.23 at the adapted step size) stay inside the skin of a list built at the
+  // start of the sweep, and the inner column (31 quads: one pass of a warp) serves every trial.
+  d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : (cfg->bulk_move ? 0.3 : 0.5));
   // outer skin (LARGE mode only): stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6
   d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 1.3;
   d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);

@@ -32,7 +32,8 @@ def main():
     for prec in (64, 32):
         fl, ms = nm.measure_fma_peak(0, prec)
         print("fma peak fp%d: %.2f TFLOP/s (%.3f ms)" % (prec, fl / 1e12, ms))
-    eng = nm.Engine(natoms=n, n_rep=ns, nt=nt, bulk_move=bool(bulk), skin=skin, skin_outer=oskin, precision=int(os.environ.get('PREC', 64)))
+    eng = nm.Engine(natoms=n, n_rep=ns, nt=nt, bulk_move=bool(bulk), skin=skin, skin_outer=oskin, precision=int(os.environ.get('PREC', 64)),
+                    mod=int(os.environ.get('MOD', 128)), ppos=float(os.environ.get('PPOS', 0.125)), pvol=float(os.environ.get('PVOL', 0.125)))
     eng.set_labels(et, pf, tt)
     t0 = time.time()
     eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(ns, .03125), dv=np.full(ns, .03125), dt=np.full(ns, .00390625))
@@ -50,6 +51,8 @@ def main():
             ct["list_pairs"] / max(1, ct["pairs_force"] + ct["pairs_full"]), sw, th[:, 17].mean(), th[:, 16].mean(), th[:, 15].mean()))
         print("   per-call clk: outer %.0f inner %.0f vel %.0f | share outer %.2f inner %.2f vel %.2f" % (ct["clk_outer"] / max(1, ct["outer_builds"] or ct["list_builds"]), ct["clk_inner"] / max(1, ct["list_builds"]), ct["clk_vel"] / max(1, ct["hmc_moves"]), ct["clk_outer"] / ct["clk_total"], ct["clk_inner"] / ct["clk_total"], ct["clk_vel"] / ct["clk_total"]))
         print("   build phases (debug build): tiles %.0f  tiles+ghost table %.0f  row walk %.0f  clk per build" % (ct["clk_outer"] / max(1, ct["list_builds"]), ct["dbg_loopit"] / max(1, ct["list_builds"]), ct["dbg_loopclk"] / max(1, ct["list_builds"])))
+        if not bulk:
+            print("   iterative PMC (debug build): rounds %d  trials/round %.1f  clk/round: evaluate %.0f commit %.0f  acc %.2f  (of the evaluate: proposals %.0f)" % (ct["reserved"], ct["pmc_trials"] / max(1, ct["reserved"]), ct["dbg_loopclk"] / max(1, ct["reserved"]), ct["dbg_loopit"] / max(1, ct["reserved"]), th[:, 15].mean(), ct["clk_vel"] / max(1, ct["reserved"])))
         print("   outer builds %d | clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["outer_builds"], ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
     clk = eng.cta_clocks().astype(float).reshape(np_, nt) / 1e6
     print("per-slot Mclk by temperature (mean over P):", np.round(clk.mean(0), 1))
