@@ -111,6 +111,20 @@ extern int nm_fail_msg(int code, const char* fmt, ...);
 
 #define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = nm_fail_msg(NM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); goto done; } } while (0)
 
+// Scratch comes from the device's stream-ordered pool with the release threshold lifted: after the first call the
+// allocations are served from the pool (no cudaMalloc / cudaFree, no device-wide synchronisation per call).
+static cudaError_t keep_pool(int device) {
+  static bool done[64] = { false };
+  if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
+  cudaMemPool_t pool;
+  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+  if (e != cudaSuccess) return e;
+  unsigned long long keep = ~0ull;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  if (e == cudaSuccess) done[device] = true;
+  return e;
+}
+
 extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const float* pos, const float* box,
                              int32_t natoms, int64_t nsamples, const double* edges, int32_t nbins, uint32_t* counts) {
   using namespace nmrdf;
@@ -139,12 +153,13 @@ extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
   p.inv_dr = (float)((nbins - 1) / (edges[nbins - 1] - edges[0]));
   {
     RCK(cudaSetDevice(device));
+    RCK(keep_pool(device));
     const size_t nposb = sizeof(float) * 3 * (size_t)natoms * nsamples, ncntb = sizeof(uint32_t) * (size_t)nbins * nsamples;
-    RCK(cudaMalloc(&d_thr, sizeof(float) * nbins));
+    RCK(cudaMallocAsync(&d_thr, sizeof(float) * nbins, st));
     RCK(cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * nbins, cudaMemcpyHostToDevice, st));
     if (dev_ptrs) { d_pos = const_cast<float*>(pos); d_box = const_cast<float*>(box); d_cnt = counts; }
     else {
-      RCK(cudaMalloc(&d_pos, nposb)); RCK(cudaMalloc(&d_box, sizeof(float) * nsamples)); RCK(cudaMalloc(&d_cnt, ncntb));
+      RCK(cudaMallocAsync(&d_pos, nposb, st)); RCK(cudaMallocAsync(&d_box, sizeof(float) * nsamples, st)); RCK(cudaMallocAsync(&d_cnt, ncntb, st));
       RCK(cudaMemcpyAsync(d_pos, pos, nposb, cudaMemcpyHostToDevice, st));
       RCK(cudaMemcpyAsync(d_box, box, sizeof(float) * nsamples, cudaMemcpyHostToDevice, st));
     }
@@ -179,8 +194,8 @@ extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
 done:
   if (rc != NM_OK) cudaStreamSynchronize(st);
   else if (!dev_ptrs) { /* already synchronised */ }
-  if (d_thr) { cudaStreamSynchronize(st); cudaFree(d_thr); }
-  if (!dev_ptrs) { if (d_pos) cudaFree(d_pos); if (d_box) cudaFree(d_box); if (d_cnt) cudaFree(d_cnt); }
+  if (d_thr) cudaFreeAsync(d_thr, st);              // stream-ordered: after the kernels that read it
+  if (!dev_ptrs) { if (d_pos) cudaFreeAsync(d_pos, st); if (d_box) cudaFreeAsync(d_box, st); if (d_cnt) cudaFreeAsync(d_cnt, st); }
 
   return rc;
 }
@@ -286,13 +301,14 @@ extern "C" int nm_cdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
   }
   {
     RCK(cudaSetDevice(device));
+    RCK(keep_pool(device));
     const size_t nb3 = (size_t)nb * nb * nb;
     const size_t nposb = sizeof(float) * 3 * (size_t)natoms * nsamples, ncntb = sizeof(uint32_t) * nb3 * nsamples;
-    RCK(cudaMalloc(&d_thr, sizeof(float) * thr.size()));
+    RCK(cudaMallocAsync(&d_thr, sizeof(float) * thr.size(), st));
     RCK(cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * thr.size(), cudaMemcpyHostToDevice, st));
     if (dev_ptrs) { d_pos = const_cast<float*>(pos); d_box = const_cast<float*>(box); d_cnt = counts; }
     else {
-      RCK(cudaMalloc(&d_pos, nposb)); RCK(cudaMalloc(&d_box, sizeof(float) * nsamples)); RCK(cudaMalloc(&d_cnt, ncntb));
+      RCK(cudaMallocAsync(&d_pos, nposb, st)); RCK(cudaMallocAsync(&d_box, sizeof(float) * nsamples, st)); RCK(cudaMallocAsync(&d_cnt, ncntb, st));
       RCK(cudaMemcpyAsync(d_pos, pos, nposb, cudaMemcpyHostToDevice, st));
       RCK(cudaMemcpyAsync(d_box, box, sizeof(float) * nsamples, cudaMemcpyHostToDevice, st));
     }
@@ -321,7 +337,7 @@ extern "C" int nm_cdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
   }
 done:
   if (rc != NM_OK) cudaStreamSynchronize(st);
-  if (d_thr) { cudaStreamSynchronize(st); cudaFree(d_thr); }
-  if (!dev_ptrs) { if (d_pos) cudaFree(d_pos); if (d_box) cudaFree(d_box); if (d_cnt) cudaFree(d_cnt); }
+  if (d_thr) cudaFreeAsync(d_thr, st);              // stream-ordered: after the kernels that read it
+  if (!dev_ptrs) { if (d_pos) cudaFreeAsync(d_pos, st); if (d_box) cudaFreeAsync(d_box, st); if (d_cnt) cudaFreeAsync(d_cnt, st); }
   return rc;
 }

@@ -332,10 +332,75 @@ static void bulk_position_mc(sim_t* s, double et, double* ntp, double* nap, doub
   }
 }
 
+/* Per-sweep candidate lists for the single-atom energy change (so that the timed CPU baseline of the iterative sweep is
+ * not an O(N^2) strawman): every atom moves at most once per sweep, by at most reach = sqrt(3) * dmax, so every atom
+ * within rc of the old or the new position of atom k at k's turn lies within R = rc + 2 reach of k at the START of the
+ * sweep. Rows hold those atoms in ASCENDING index order: the sum visits the same non-zero terms in the same order as
+ * the all-atom loop of lj_delta_atom, i.e. the result is bitwise identical (tests/test_oracle_lj.py). */
+static int g_delta_lists = 1;
+ORC_API void orc_set_delta_lists(int on) { g_delta_lists = on; }
+static int cmp_int(const void* a, const void* b) { int x = *(const int*)a, y = *(const int*)b; return (x > y) - (x < y); }
+typedef struct { int* start; int* idx; } dlist_t;
+static int dlist_build(dlist_t* dl, int n, const double* x, double L, double R) {
+  int nc = (int)floor(L / R);
+  if (nc < 3) return 0;
+  double hL = 0.5 * L, R2 = R * R;
+  int ncell = nc * nc * nc;
+  int* head = (int*)malloc(sizeof(int) * ncell); int* next = (int*)malloc(sizeof(int) * n); int* cidx = (int*)malloc(sizeof(int) * n);
+  for (int c = 0; c < ncell; c++) head[c] = -1;
+  for (int i = n - 1; i >= 0; i--) {
+    int cx = (int)(x[3 * i] / L * nc), cy = (int)(x[3 * i + 1] / L * nc), cz = (int)(x[3 * i + 2] / L * nc);
+    if (cx >= nc) cx = nc - 1; if (cy >= nc) cy = nc - 1; if (cz >= nc) cz = nc - 1;
+    if (cx < 0) cx = 0; if (cy < 0) cy = 0; if (cz < 0) cz = 0;
+    int c = (cx * nc + cy) * nc + cz; cidx[i] = c; next[i] = head[c]; head[c] = i;
+  }
+  dl->start = (int*)malloc(sizeof(int) * (n + 1));
+  dl->idx = NULL;
+  for (int pass = 0; pass < 2; pass++) {
+    int tot = 0;
+    for (int i = 0; i < n; i++) {
+      int cnt = 0, cx = cidx[i] / (nc * nc), cy = (cidx[i] / nc) % nc, cz = cidx[i] % nc;
+      if (pass) tot = dl->start[i];
+      for (int ax = -1; ax <= 1; ax++) for (int ay = -1; ay <= 1; ay++) for (int az = -1; az <= 1; az++) {
+        int c = (((cx + ax + nc) % nc) * nc + (cy + ay + nc) % nc) * nc + (cz + az + nc) % nc;
+        for (int j = head[c]; j >= 0; j = next[j]) {
+          if (j == i) continue;
+          double dx = mic(x[3 * i] - x[3 * j], L, hL), dy = mic(x[3 * i + 1] - x[3 * j + 1], L, hL), dz = mic(x[3 * i + 2] - x[3 * j + 2], L, hL);
+          if (dx * dx + dy * dy + dz * dz < R2) { if (pass) dl->idx[tot + cnt] = j; cnt++; }
+        }
+      }
+      if (!pass) { dl->start[i] = tot; tot += cnt; if (i == n - 1) dl->start[n] = tot; }
+      else qsort(dl->idx + dl->start[i], cnt, sizeof(int), cmp_int);
+    }
+    if (!pass) dl->idx = (int*)malloc(sizeof(int) * (dl->start[n] > 0 ? dl->start[n] : 1));
+  }
+  free(head); free(next); free(cidx);
+  return 1;
+}
+static double lj_delta_atom_rows(const dlist_t* dl, const double* x, int k, const double xn[3], double L, double rc, int64_t* nvis) {
+  double rc2 = rc * rc, hL = 0.5 * L, de = 0.0;
+  for (int q = dl->start[k]; q < dl->start[k + 1]; q++) {
+    int j = dl->idx[q];
+    double ro = 0, rn = 0;
+    for (int c = 0; c < 3; c++) {
+      double d0 = mic(x[3 * k + c] - x[3 * j + c], L, hL), d1 = mic(xn[c] - x[3 * j + c], L, hL);
+      ro += d0 * d0; rn += d1 * d1;
+    }
+    if (rn < rc2) { double r2 = 1.0 / rn, r6 = r2 * r2 * r2; de += r6 * (4.0 * r6 - 4.0); if (nvis) (*nvis)++; }
+    if (ro < rc2) { double r2 = 1.0 / ro, r6 = r2 * r2 * r2; de -= r6 * (4.0 * r6 - 4.0); if (nvis) (*nvis)++; }
+  }
+  return de;
+}
+
 /* a-8 iter_position_mc, lammps_remcmc.py:505-549. The reference re-evaluates the whole system
  * per trial; E_tot' - E_tot is the single-atom energy change, computed directly here. */
 static void iter_position_mc(sim_t* s, double et, double* ntp, double* nap, double dx, const rng_t* r) {
   int n = s->n; double box = s->box;
+  dlist_t dl; int have = 0;
+  if (g_delta_lists && n >= 256) {
+    double dmax = fabs(dx * s->p->lat_scale), R = s->p->rc + 2.0 * sqrt(3.0) * dmax * (1.0 + 1e-9) + 1e-9;
+    have = dlist_build(&dl, n, s->x, box, R);
+  }
   for (int k = 0; k < n; k++) {
     *ntp += 1;
     double u[3], nd[3]; rng_uniform3(r, (uint32_t)k, P_ITER_DISP, u);
@@ -345,14 +410,15 @@ static void iter_position_mc(sim_t* s, double et, double* ntp, double* nap, doub
       nd[c] = wrap1(nd[c], box);                                /* the following 'run 0' remap */
     }
     int64_t nvis = 0;
-    double de = lj_delta_atom(n, s->x, k, nd, box, s->p->rc, &nvis) / et;
+    double de = (have ? lj_delta_atom_rows(&dl, s->x, k, nd, box, s->p->rc, &nvis) : lj_delta_atom(n, s->x, k, nd, box, s->p->rc, &nvis)) / et;
     s->ct[CT_PAIRS_DELTA] += (uint64_t)nvis; s->ct[CT_PMC_TRIALS]++;
     if (metropolis(de, r, (uint32_t)k, P_ITER_ACC)) {
       *nap += 1; for (int c = 0; c < 3; c++) s->x[3 * k + c] = nd[c];
     }
   }
+  if (have) { free(dl.start); free(dl.idx); }
   s->ct[CT_PMC_MOVES]++;
-  run0(s);                                                      /* state the last 'run 0' leaves */
+  run0(s);                                                      /* state the last 'run 0' of the sweep leaves */
 }
 
 /* a-6 volume_mc, lammps_remcmc.py:552-595 */

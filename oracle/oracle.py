@@ -116,6 +116,11 @@ def lj_eval_numpy(x, box, rc=2.5):
     return pe, w, f, int(mask.sum())
 
 
+def set_delta_lists(on):
+    """iterative PMC: per-sweep candidate lists (default, bitwise identical results) or the plain all-atom sum"""
+    lib().orc_set_delta_lists(C.c_int(int(bool(on))))
+
+
 def lj_delta_atom(x, k, xn, box, rc=2.5):
     x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
     xn = np.ascontiguousarray(xn, dtype=np.float64)

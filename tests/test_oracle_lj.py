@@ -119,3 +119,24 @@ def test_lammps_melt_example_step0_pins_the_oracle(orc):
         assert np.abs(f).max() < 1e-11
     e, wn, nn = orc.fcc_shell_sum(a)
     assert abs(e - MELT_EPAIR) < 5e-8 and npairs == n * nn // 2
+
+
+def test_iterative_sweep_candidate_lists_are_bitwise_identical_to_the_all_atom_sum(orc):
+    """the per-sweep candidate lists of the oracle's iter_position_mc (what the timed CPU baseline of C4 runs) visit the
+    same non-zero terms in the same order as the O(N) loop: identical positions, energies and counters, bit for bit"""
+    n_side, n = 6, 864
+    rng = np.random.default_rng(3)
+    box = orc.round6(n_side * (4 / 0.85) ** (1 / 3))
+    x0 = orc.wrap((orc.fcc_positions(n_side, box) + rng.normal(0, 0.08, (n, 3))).reshape(-1), box)
+    params = orc.make_params(mod=3, bulk_move=0, ppos=1.0, pvol=0.0, seed=99)
+    label = np.array([1.2, 2.0 / 1.2, 1.2, 1.2])
+    out = []
+    for lists in (1, 0):
+        orc.set_delta_lists(lists)
+        x, v = x0.copy(), np.zeros(3 * n)
+        scal = np.array([box, 0.09, 0.03125, 0.00390625])
+        th, ct = orc.cycle(params, label, 5, 0, x, v, scal, np.zeros(6))
+        out.append((x, th, ct))
+    orc.set_delta_lists(1)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    assert 0 < out[0][1][10] < out[0][1][9]          # accepted and rejected trials
