@@ -322,7 +322,7 @@ def run_b200(args):
     if not args.no_legs and args.workload == "c2":
         # short legs of the other BASELINE configurations, same process, same box (driver-run evidence for C3 / C4 / C5)
         legs = {}
-        for wl, (st_, wu_, eq_) in (("c3", (3, 3, 12)), ("c4", (24, 8, 24))):
+        for wl, (st_, wu_, eq_) in (("c3", (3, 3, 32)), ("c4", (24, 8, 64))):     # equilibrated like the headline (stationary step sizes)
             o, _ = measure_mc(args, comm, torch, wl, st_, wu_, eq_, with_e2e=True, with_gate=True)
             if o is not None:
                 legs[wl] = leg_summary(o)

@@ -86,6 +86,7 @@ struct Dev {
                                            // [1 + nrep] CTAs arrived, [2 + nrep] placement invalid, [3 + nrep + smid] CTAs on SM smid
   int nseg, seg_moves;                     // a cycle is cut into nseg segments of seg_moves moves (the unit of scheduling)
   int place;                               // 1: first ticket of every CTA from the SM-aware placement (placement_rank)
+  int list_pf;                             // force loop: prefetch the list row this many rows past the one being loaded into L1 (-1: off)
   int *status;                             // [nrep]
   // per local slot
   double *label;                           // [nrep][4] et pf temp temp_vel
@@ -914,11 +915,25 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
 #else
     uint2 cur = *reinterpret_cast<const uint2*>(lp);
     lp += stride;
-    for (int q = 0; q < nq; q++) {
-      const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // for the next iteration
-      lp += stride;
-      do_quad(cur);
-      cur = nxt;
+    // ptxas sinks the load of the next quad to the end of the iteration (its registers serve as temporaries in between), so
+    // the load itself hides nothing: the row list_pf rows further down is pulled into L1 by a prefetch (no destination
+    // register, nothing to sink), and the late load hits L1 instead of waiting for L2 / HBM
+    if (d.list_pf >= 0) {
+      const size_t pf_off = (size_t)d.list_pf * stride;
+      for (int q = 0; q < nq; q++) {
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(lp + pf_off));
+        const uint2 nxt = *reinterpret_cast<const uint2*>(lp);
+        lp += stride;
+        do_quad(cur);
+        cur = nxt;
+      }
+    } else {
+      for (int q = 0; q < nq; q++) {
+        const uint2 nxt = *reinterpret_cast<const uint2*>(lp);   // for the next iteration
+        lp += stride;
+        do_quad(cur);
+        cur = nxt;
+      }
     }
 #endif
 #ifdef NM_DEBUG_LOOPCLOCKS   // per-atom loop clocks of thread 0 (tools/probe.py); compiled out of the product build
@@ -2149,6 +2164,11 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     if (seg_moves <= 0 || seg_moves > d.mod) seg_moves = d.mod > 0 ? d.mod : 1;
     d.seg_moves = seg_moves;
     d.nseg = d.mod > 0 ? (d.mod + seg_moves - 1) / seg_moves : 1;
+    // measured (B200): N = 4000 (lists streamed from HBM by every evaluation) 140.7 -> 135.5 ms per C3 step with the row being
+    // loaded prefetched; N = 500 (lists mostly L2-resident) 43.4 -> 43.7 ms: off there
+    d.list_pf = d.small ? -1 : 0;
+    if (const char* ev = getenv("NM_LIST_PF")) d.list_pf = atoi(ev);
+    if (d.list_pf > LIST_SPARE_ROWS - 2) d.list_pf = LIST_SPARE_ROWS - 2;      // stays inside the spare rows of the list buffer
     d.place = occ == 2 && nrep > h->nsm && nrep <= slots && h->nsm <= SMID_MAX && !getenv("NM_NO_PLACEMENT");
   }
   *out = h;
