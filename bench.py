@@ -534,14 +534,23 @@ def run_rdf(args, comm=None, steps=None, nsamples=None):
 
 def main():
     args = parse()
+    # rank 0 prints ONE JSON line on stdout: libraries that write there (NCCL's version banner) are sent to stderr for the
+    # duration of the run, the line goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     if args.workload == "c5":
         out = run_rdf(args) if args.impl != "reference" else None
         if out is not None:
-            print(json.dumps(out))
+            emit(out)
         return
     out = run_reference(args) if args.impl == "reference" else run_b200(args)
     if out is not None:
-        print(json.dumps(out))
+        emit(out)
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():

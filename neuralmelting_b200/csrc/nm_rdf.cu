@@ -24,9 +24,12 @@ constexpr int T = 256;
 
 struct RdfParams {
   const float* pos; const float* box; uint32_t* counts;
-  const float* thr;            // [nb] float32 lower thresholds: (double)d >= edge[k]  <=>  d >= thr[k]
+  const float* thr;            // [2][nb]: float32 lower thresholds, (double)d >= edge[k]  <=>  d >= thr[k]; then the same
+                               // thresholds on the SQUARED distance: fl(sqrt(s2)) >= thr[k]  <=>  s2 >= thr[nb + k] (exact: sqrt.rn is
+                               // monotone, the host finds the smallest such float), thr[2 nb - 1] = +inf (last bin right-closed)
   int N, nb, a_chunk, private_hist;
   float t_top, cut, inv_dr;    // d <= t_top <=> (double)d <= edge[nb-1]; prune |delta| > cut
+  float t2_top;                // fl(sqrt(s2)) <= t_top  <=>  s2 <= t2_top
 };
 
 __device__ __forceinline__ void count_one(float dx, float dy, float dz, const RdfParams& p, const float* sthr,
@@ -47,18 +50,55 @@ __device__ __forceinline__ void count_one(float dx, float dy, float dz, const Rd
 
 __global__ void __launch_bounds__(T) k_rdf(RdfParams p) {
   extern __shared__ __align__(16) unsigned char sm[];
-  float* ax = reinterpret_cast<float*>(sm);
-  float* ay = ax + p.a_chunk; float* az = ay + p.a_chunk;
-  float* sthr = az + p.a_chunk;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(sthr + p.nb);
+  float4* a4 = reinterpret_cast<float4*>(sm);
+  float* sthr = reinterpret_cast<float*>(a4 + p.a_chunk);
+  float* st2 = sthr + p.nb;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(st2 + p.nb);
   const int s = blockIdx.y, a0 = blockIdx.x * p.a_chunk, na = min(p.N, a0 + p.a_chunk) - a0;
   const float* ps = p.pos + (size_t)s * p.N * 3;
-  for (int a = threadIdx.x; a < na; a += T) { ax[a] = ps[3 * (a0 + a)]; ay[a] = ps[3 * (a0 + a) + 1]; az[a] = ps[3 * (a0 + a) + 2]; }
-  for (int k = threadIdx.x; k < p.nb; k += T) sthr[k] = p.thr[k];
+  for (int a = threadIdx.x; a < na; a += T) a4[a] = make_float4(ps[3 * (a0 + a)], ps[3 * (a0 + a) + 1], ps[3 * (a0 + a) + 2], 0.f);
+  for (int k = threadIdx.x; k < 2 * p.nb; k += T) sthr[k] = p.thr[k];
   const int nh = p.private_hist ? p.nb * T / 2 : p.nb;     // private columns are 16-bit (two per word)
   for (int k = threadIdx.x; k < nh; k += T) hist[k] = 0u;
   __syncthreads();
   const float bx = p.box[s], nbx = __fmul_rn(bx, -1.0f), cut = p.cut;
+  // FAST path (box >= 2 cut (1 + 1e-5), private columns): along an axis at most ONE of the three images can land inside the
+  // last edge, the one nearest to the unshifted difference d0 = a - b (the others are at least box/2 - rounding > cut away),
+  // so it is picked from d0 alone and only ITS difference is formed -- with the reference's own operations,
+  // a - fl(b + fl(box * s)). Every pair then goes through the squared distance s2 (same three products and two sums as the
+  // reference) and is binned ON s2 against thresholds that are exactly equivalent to the reference's tests on
+  // fl(sqrt(s2)) (no sqrt.rn); the first guess of the bin comes from an approximate square root and is verified.
+  if (p.private_hist && bx >= 2.0f * cut * (1.0f + 1e-5f)) {
+    const float hb = 0.5f * bx, t0 = sthr[0], t2lo = st2[0], t2top = p.t2_top, inv_dr = p.inv_dr;
+    const int kmax = p.nb - 2;
+    unsigned short* col = reinterpret_cast<unsigned short*>(hist) + threadIdx.x;
+    for (int b = threadIdx.x; b < p.N; b += T) {
+      const float px = ps[3 * b], py = ps[3 * b + 1], pz = ps[3 * b + 2];
+      const float xm = __fadd_rn(px, nbx), xp = __fadd_rn(px, bx);
+      const float ym = __fadd_rn(py, nbx), yp = __fadd_rn(py, bx);
+      const float zm = __fadd_rn(pz, nbx), zp = __fadd_rn(pz, bx);
+#pragma unroll 2
+      for (int a = 0; a < na; a++) {
+        const float4 q = a4[a];
+        const float dx0 = __fsub_rn(q.x, px), dy0 = __fsub_rn(q.y, py), dz0 = __fsub_rn(q.z, pz);
+        const float xs = fabsf(dx0) > hb ? (dx0 > 0.f ? xp : xm) : px;
+        const float ys = fabsf(dy0) > hb ? (dy0 > 0.f ? yp : ym) : py;
+        const float zs = fabsf(dz0) > hb ? (dz0 > 0.f ? zp : zm) : pz;
+        const float dx = __fsub_rn(q.x, xs), dy = __fsub_rn(q.y, ys), dz = __fsub_rn(q.z, zs);
+        const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (s2 >= t2lo && s2 <= t2top) {
+          float dq; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(dq) : "f"(s2));
+          int k = (int)((dq - t0) * inv_dr);
+          k = max(0, min(k, kmax));
+          if (s2 < st2[k] || s2 >= st2[k + 1]) {             // the guess is off (rounding at an edge, non-uniform edges)
+            while (k > 0 && s2 < st2[k]) k--;
+            while (k < kmax && s2 >= st2[k + 1]) k++;
+          }
+          col[k * T]++;
+        }
+      }
+    }
+  } else
   for (int b = threadIdx.x; b < p.N; b += T) {
     // the three images of atom b along each axis: pos_b + box*s, s = -1, 0, +1 (lammps_distr.py:130)
     const float px = ps[3 * b], py = ps[3 * b + 1], pz = ps[3 * b + 2];
@@ -66,7 +106,7 @@ __global__ void __launch_bounds__(T) k_rdf(RdfParams p) {
     const float ym = __fadd_rn(py, nbx), yp = __fadd_rn(py, bx);
     const float zm = __fadd_rn(pz, nbx), zp = __fadd_rn(pz, bx);
     for (int a = 0; a < na; a++) {
-      const float qx = ax[a], qy = ay[a], qz = az[a];
+      const float qx = a4[a].x, qy = a4[a].y, qz = a4[a].z;
       const float dx0 = __fsub_rn(qx, px), dxm = __fsub_rn(qx, xm), dxp = __fsub_rn(qx, xp);
       const float dy0 = __fsub_rn(qy, py), dym = __fsub_rn(qy, ym), dyp = __fsub_rn(qy, yp);
       const float dz0 = __fsub_rn(qz, pz), dzm = __fsub_rn(qz, zm), dzp = __fsub_rn(qz, zp);
@@ -138,7 +178,7 @@ extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
   int rc = NM_OK;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   float *d_pos = nullptr, *d_box = nullptr, *d_thr = nullptr; uint32_t* d_cnt = nullptr;
-  std::vector<float> thr(nbins);
+  std::vector<float> thr(2 * (size_t)nbins);
   // float32 thresholds exactly equivalent to the float64 edge tests of np.histogram
   for (int k = 0; k < nbins; k++) {
     float f = (float)edges[k];
@@ -147,16 +187,32 @@ extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
   }
   float t_top = (float)edges[nbins - 1];
   if ((double)t_top > edges[nbins - 1]) t_top = nextafterf(t_top, -INFINITY);
+  // ... and on the squared distance: sqrtf is correctly rounded, hence monotone, so "fl(sqrt(s2)) >= t" holds from one float on
+  // (smallest s2 found by stepping around t*t), and "fl(sqrt(s2)) <= t_top" up to one float
+  auto t2_ge = [](float t) -> float {
+    if (!(t > 0.0f)) return 0.0f;
+    float s2 = t * t;
+    while (s2 > 0.0f && sqrtf(nextafterf(s2, -INFINITY)) >= t) s2 = nextafterf(s2, -INFINITY);
+    while (sqrtf(s2) < t) s2 = nextafterf(s2, INFINITY);
+    return s2;
+  };
+  for (int k = 0; k < nbins - 1; k++) thr[nbins + k] = t2_ge(thr[k]);
+  thr[2 * (size_t)nbins - 1] = INFINITY;
+  float t2_top = t_top > 0.0f ? t_top * t_top : 0.0f;
+  if (t_top > 0.0f) {
+    while (sqrtf(nextafterf(t2_top, INFINITY)) <= t_top) t2_top = nextafterf(t2_top, INFINITY);
+    while (t2_top > 0.0f && sqrtf(t2_top) > t_top) t2_top = nextafterf(t2_top, -INFINITY);
+  }
   RdfParams p;
-  p.N = natoms; p.nb = nbins; p.t_top = t_top;
+  p.N = natoms; p.nb = nbins; p.t_top = t_top; p.t2_top = t2_top;
   p.cut = t_top * (1.0f + 4e-6f) + 1e-30f;
   p.inv_dr = (float)((nbins - 1) / (edges[nbins - 1] - edges[0]));
   {
     RCK(cudaSetDevice(device));
     RCK(keep_pool(device));
     const size_t nposb = sizeof(float) * 3 * (size_t)natoms * nsamples, ncntb = sizeof(uint32_t) * (size_t)nbins * nsamples;
-    RCK(cudaMallocAsync(&d_thr, sizeof(float) * nbins, st));
-    RCK(cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * nbins, cudaMemcpyHostToDevice, st));
+    RCK(cudaMallocAsync(&d_thr, sizeof(float) * thr.size(), st));
+    RCK(cudaMemcpyAsync(d_thr, thr.data(), sizeof(float) * thr.size(), cudaMemcpyHostToDevice, st));
     if (dev_ptrs) { d_pos = const_cast<float*>(pos); d_box = const_cast<float*>(box); d_cnt = counts; }
     else {
       RCK(cudaMallocAsync(&d_pos, nposb, st)); RCK(cudaMallocAsync(&d_box, sizeof(float) * nsamples, st)); RCK(cudaMallocAsync(&d_cnt, ncntb, st));
@@ -169,12 +225,12 @@ extern "C" int nm_rdf_counts(int device, void* cuda_stream, int dev_ptrs, const 
     if (nsamples < 2 * 148) nsplit = (int)((2 * 148 + nsamples - 1) / nsamples);
     int a_chunk = (natoms + nsplit - 1) / nsplit;
     if (a_chunk < 64) a_chunk = natoms < 64 ? natoms : 64;
-    if (a_chunk > 1024) a_chunk = 1024;      // 12 KB of positions + 32 KB of 16-bit private histogram columns: five CTAs per SM
+    if (a_chunk > 1024) a_chunk = 1024;      // 16 KB of positions + 32 KB of 16-bit private histogram columns: four CTAs per SM
     // a thread counts at most a_chunk * ceil(natoms / T) pairs: keep that inside 16 bits
     { const int per_thread = (natoms + T - 1) / T; if ((long long)a_chunk * per_thread > 65535) a_chunk = 65535 / per_thread; if (a_chunk < 1) a_chunk = 1; }
     nsplit = (natoms + a_chunk - 1) / a_chunk;
     p.a_chunk = a_chunk;
-    const size_t base = sizeof(float) * (3 * (size_t)a_chunk + nbins);
+    const size_t base = sizeof(float) * (4 * (size_t)a_chunk + 2 * (size_t)nbins);
     p.private_hist = (base + sizeof(unsigned short) * (size_t)nbins * T) <= 200 * 1024 && (nbins * T) % 2 == 0;
     const size_t smem = base + (p.private_hist ? sizeof(unsigned short) * (size_t)nbins * T : sizeof(uint32_t) * (size_t)nbins);
     RCK(cudaFuncSetAttribute(k_rdf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

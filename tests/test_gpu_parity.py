@@ -336,6 +336,29 @@ def test_rdf_large_sample_property(nm, orc):
     np.testing.assert_array_equal(got[0], orc.rdf_counts(pos[0], box, r))
 
 
+def test_rdf_fast_and_generic_paths_on_arbitrary_edges(nm, orc):
+    """the kernel bins on the SQUARED distance with exactly equivalent thresholds when the box is at least twice the last edge
+    (one admissible image per axis) and on sqrt.rn distances with all 27 images otherwise: both against the oracle, with
+    non-uniform edges (the bin guess must be repaired), edges that start at 0, a top edge above half of the smallest box
+    (two admissible images: generic path) and atoms outside the box"""
+    rng = np.random.default_rng(11)
+    n = 300
+    box = np.array([8.0, 8.000001, 9.5, 12.25, 31.0], dtype=np.float32)
+    pos = (rng.uniform(-0.1, 1.1, (box.size, n, 3)) * box[:, None, None]).astype(np.float32)
+    for top in (3.9, 4.0, 4.6):
+        for sb in (3, 17, 64):
+            for shape in ("uniform", "quadratic", "random"):
+                u = np.linspace(0.0, 1.0, sb)
+                if shape == "quadratic":
+                    u = u ** 2
+                elif shape == "random":
+                    u = np.concatenate([[0.0], np.sort(rng.uniform(0.0, 1.0, sb - 2)), [1.0]])
+                r = u * top
+                got = nm.rdf_counts(pos, box, r)
+                for s in range(box.size):
+                    np.testing.assert_array_equal(got[s], orc.rdf_counts(pos[s], box[s], r), err_msg="top %g sb %d %s sample %d" % (top, sb, shape, s))
+
+
 # ------------------------------------------------------------------ (e) sharding: N ranks == 1 rank
 @pytest.mark.parametrize("layout", ["cyclic", "blocks"])
 def test_row_sharded_engines_reproduce_the_single_engine_run(nm, orc, layout):
