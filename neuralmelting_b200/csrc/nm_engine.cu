@@ -5,6 +5,7 @@
 // NSTPS velocity-Verlet steps of an HMC trajectory, the Metropolis tests and the counters
 // happen on chip. Replaces the per-replica LAMMPS instance of lammps_remcmc.py:459-691.
 // FP64 FMA pipe is the roofline (no tensor cores: not a dense contraction).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -109,6 +110,7 @@ struct Ctx {
   uint32_t* ginfo_g;            // global copies of the ghost table, one per list buffer
   uint8_t* gtbl;                // shared (SMALL mode): rank of image subset g among the subsets of a near-face mask, [8][8]
   uint16_t* gidx;               // shared (SMALL mode): [Npad][8] index of the copy of atom j for image subset g (g = 0: j itself)
+  uint4* hp;                    // shared (SMALL mode): [Npad/2] half-precision fractional coordinates of atoms 2k, 2k+1 packed (x2, y2, z2, -): tile tests
   int* iscan;                   // shared: block-scan scratch (34 ints)
   double *red, *bc;             // reduction scratch, broadcast scratch
   int *cell_cnt, *cell_start, *ibc;
@@ -143,7 +145,7 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
   b += sizeof(unsigned long long) * (2 + NM_COUNTER_WIDTH);
   b += sizeof(float4) * (size_t)Npad;
   b += sizeof(int) * (8 + 2 + 34);                              // ibc, iscan (44 ints: keeps 16-byte alignment)
-  if (small) b += sizeof(uint32_t) * (size_t)Npad + 64 + sizeof(uint16_t) * 8 * (size_t)Npad;   // ghost table, subset-rank table, copy index table
+  if (small) b += sizeof(uint32_t) * (size_t)Npad + 64 + sizeof(uint16_t) * 8 * (size_t)Npad + sizeof(uint4) * (size_t)(Npad / 2);   // ghost table, subset-rank table, copy index table, packed half copies
   else {
     b += sizeof(int) * 2 * (NCMAX * NCMAX * NCMAX + 1);         // cell counts / starts
     b += sizeof(uint16_t) * (size_t)Npad;                       // cell members
@@ -186,6 +188,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.iscan = q; q += 34;
   if (d.small) {
     cx.gidx = reinterpret_cast<uint16_t*>(q); q += 4 * d.Npad;        // first: 16-byte aligned rows
+    cx.hp = reinterpret_cast<uint4*>(q); q += 2 * d.Npad;             // (Npad / 2) x 16 bytes
     cx.ginfo = reinterpret_cast<uint32_t*>(q); q += d.Npad;
     cx.gtbl = reinterpret_cast<uint8_t*>(q);
     cx.cell_cnt = cx.cell_start = nullptr; cx.cell_atoms = nullptr; cx.gcur = nullptr;
@@ -201,7 +204,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
     cx.cell_start = q; q += NCMAX * NCMAX * NCMAX + 1;
     cx.cell_atoms = reinterpret_cast<uint16_t*>(q);
     cx.gcur = cx.cell_atoms + d.Npad;
-    cx.ginfo = nullptr; cx.gtbl = nullptr; cx.gidx = nullptr;
+    cx.ginfo = nullptr; cx.gtbl = nullptr; cx.gidx = nullptr; cx.hp = nullptr;
   }
   cx.hbT = d.small ? d.hbT + (size_t)c * (d.Npad / 32) * d.Npad : nullptr;
   cx.ginfo_g = d.small ? d.ginfo + (size_t)c * 2 * d.Npad : nullptr;
@@ -505,37 +508,74 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
   __syncthreads();
   wrap_and_refresh(cx, true);
   __syncthreads();
-  // ---- (1) tiles
+  // ---- (1) tiles, two pair tests per instruction: the columns of a tile are taken two at a time from half-precision
+  // copies of the (centred) fractional coordinates, packed per atom pair. The half arithmetic errs by < 1.2 % on the
+  // squared separation of a pair near the list radius (inputs 2^-13 each, three roundings of 2^-12 per axis, the
+  // products and sums 2^-11 relative), so the threshold is raised by that much: the matrix stays a superset of the
+  // exact list (1.7 % more listed pairs than the float32 test), and it is symmetric bit for bit (|a - b| = |b - a|).
   const long long t_tiles0 = clock64();
+  for (int k = tid; k < Npad / 2; k += blockDim.x) {
+    const float4 a = cx.sf[2 * k], b = cx.sf[2 * k + 1];
+    const bool da = 2 * k >= N, db = 2 * k + 1 >= N;                 // parked entries: far away, finite
+    const __half2 hx = __floats2half2_rn(da ? 100.f : a.x - 0.5f, db ? 100.f : b.x - 0.5f);
+    const __half2 hy = __floats2half2_rn(da ? 100.f : a.y - 0.5f, db ? 100.f : b.y - 0.5f);
+    const __half2 hz = __floats2half2_rn(da ? 100.f : a.z - 0.5f, db ? 100.f : b.z - 0.5f);
+    cx.hp[k] = make_uint4(*reinterpret_cast<const unsigned*>(&hx), *reinterpret_cast<const unsigned*>(&hy), *reinterpret_cast<const unsigned*>(&hz), 0u);
+  }
+  __syncthreads();
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
   const int ntile = W * (W + 1) / 2;
   const uint32_t lastmask = (N & 31) ? (1u << (N & 31)) - 1u : 0xffffffffu;
+  unsigned thr2;
+  {
+    __half t = __float2half_ru((float)(rl * rl * invL * invL * 1.012));
+    const __half2 t2 = __halves2half2(t, t);
+    thr2 = *reinterpret_cast<const unsigned*>(&t2);
+  }
+  const __half2 one2 = __floats2half2_rn(1.f, 1.f);
+  uint32_t* colbuf = reinterpret_cast<uint32_t*>(cx.red) + 32 * wid;   // the warp's 32 column ballots of a tile (scratch is free here)
   for (int t = wid; t < ntile; t += nw) {
     int ti = 0, rem = t;                      // tile (ti, tj), ti <= tj, enumerated row by row
     while (rem >= W - ti) { rem -= W - ti; ti++; }
     const int tj = ti + rem;
     const int i = ti * 32 + lane;             // < Npad (Npad >= 32 W); rows >= N are never read
-    const float4 pi = cx.sf[i];
-    const unsigned pj_s = (unsigned)__cvta_generic_to_shared(cx.sf + tj * 32);
-    uint32_t mask = 0, mycol = 0;
-    // fractional coordinates lie in [0,1]: the nearest-image distance along an axis is min(|d|, 1 - |d|), the same
-    // value as d - rint(d) gives, in two instructions; the test is symmetric in (i, j) bit for bit
-#pragma unroll
-    for (int jj = 0; jj < 32; jj++) {
-      float4 pj;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pj.x), "=f"(pj.y), "=f"(pj.z), "=f"(pj.w) : "r"(pj_s + 16u * jj));
-      float ax = fabsf(pi.x - pj.x), ay = fabsf(pi.y - pj.y), az = fabsf(pi.z - pj.z);
-      ax = fminf(ax, 1.f - ax); ay = fminf(ay, 1.f - ay); az = fminf(az, 1.f - az);
-      const bool hit = fmaf(az, az, fmaf(ay, ay, ax * ax)) < rl2f;
-      const uint32_t col = __ballot_sync(0xffffffffu, hit);   // column jj of the tile = row (tj*32+jj), word ti
-      if (hit) mask |= 1u << jj;
-      if (lane == jj) mycol = col;
+    __half2 xi, yi, zi;
+    {
+      const uint4 me = cx.hp[i >> 1];
+      const __half2 mx = *reinterpret_cast<const __half2*>(&me.x), my = *reinterpret_cast<const __half2*>(&me.y), mz = *reinterpret_cast<const __half2*>(&me.z);
+      xi = (i & 1) ? __high2half2(mx) : __low2half2(mx); yi = (i & 1) ? __high2half2(my) : __low2half2(my); zi = (i & 1) ? __high2half2(mz) : __low2half2(mz);
     }
+    const unsigned pj_s = (unsigned)__cvta_generic_to_shared(cx.hp + tj * 16);
+    const unsigned cb_s = (unsigned)__cvta_generic_to_shared(colbuf);
+    uint32_t mask = 0;
+    __syncwarp();                             // the previous tile's column reads are done
+#pragma unroll
+    for (int j2 = 0; j2 < 16; j2++) {
+      unsigned px, py, pz, pw;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(px), "=r"(py), "=r"(pz), "=r"(pw) : "r"(pj_s + 16u * j2));
+      // nearest-image separation along an axis = min(|d|, 1 - |d|) (coordinates in [-1/2, 1/2])
+      __half2 ax = __habs2(__hsub2(xi, *reinterpret_cast<const __half2*>(&px)));
+      __half2 ay = __habs2(__hsub2(yi, *reinterpret_cast<const __half2*>(&py)));
+      __half2 az = __habs2(__hsub2(zi, *reinterpret_cast<const __half2*>(&pz)));
+      ax = __hmin2(ax, __hsub2(one2, ax)); ay = __hmin2(ay, __hsub2(one2, ay)); az = __hmin2(az, __hsub2(one2, az));
+      const __half2 r2 = __hfma2(az, az, __hfma2(ay, ay, __hmul2(ax, ax)));
+      // columns 2 j2 and 2 j2 + 1 of the tile = rows (tj*32 + 2 j2 [+ 1]), word ti: two ballots, own bits into the row mask,
+      // lane 0 parks the ballots for the transposed write
+      asm volatile("{\n\t.reg .pred p, q, z;\n\t.reg .b32 c0, c1;\n\tsetp.lt.f16x2 p|q, %1, %2;\n\tsetp.ne.b32 z, %5, 0;\n\t"
+                   "vote.sync.ballot.b32 c0, p, 0xffffffff;\n\tvote.sync.ballot.b32 c1, q, 0xffffffff;\n\t"
+                   "@p or.b32 %0, %0, %3;\n\t@q or.b32 %0, %0, %4;\n\t"
+                   "@z st.shared.v2.u32 [%6], {c0, c1};\n\t}"
+                   : "+r"(mask) : "r"(*reinterpret_cast<const unsigned*>(&r2)), "r"(thr2), "r"(1u << (2 * j2)), "r"(2u << (2 * j2)),
+                     "r"((int)(lane == 0)), "r"(cb_s + 8u * j2) : "memory");
+    }
+    __syncwarp();
+    const uint32_t mycol = colbuf[lane];
     if (tj == W - 1) mask &= lastmask;        // padded columns
     if (ti == tj) mask &= ~(1u << lane);      // self
     cx.hbT[(size_t)tj * Npad + i] = mask;                                  // row i, word tj
     if (ti != tj) cx.hbT[(size_t)ti * Npad + tj * 32 + lane] = mycol;      // row tj*32+lane, word ti (rows >= N: never read)
   }
+  (void)rl2f;
   // ---- ghost table (independent of the tiles)
   const bool own = tid < N;
   const float rg = (float)(rl * invL * (1.0 + 1e-3));
