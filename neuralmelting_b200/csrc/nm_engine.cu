@@ -455,7 +455,12 @@ __device__ __forceinline__ void walk_hit_row(const Dev& d, Ctx& cx, int i, const
   const unsigned rowbytes = (unsigned)Npad * 8u, cap = 4u * (unsigned)d.maxq;
   const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf), gx_s = (unsigned)__cvta_generic_to_shared(cx.gidx);
   const uint32_t* hrow = cx.hbT + i;
-  unsigned pos = 0;
+  // Hits are pushed into a 128-bit shift register (stored XOR N, so that empty fields read as the parked dummy atom);
+  // one 8-byte store per completed quad: a warp's rows advance at different rates, and a 2-byte store per hit costs a
+  // sector write per lane -- the walk was bound by those.
+  const unsigned long long dummy4 = 0x0001000100010001ull * (unsigned long long)N;
+  unsigned pos = 0, fill = 0, oq = 0;
+  unsigned long long acc = 0ull;
   int w = 0;
   uint32_t m = hrow[0], mnext = W > 1 ? hrow[Npad] : 0u;            // the next word is in flight while this one is walked
   for (;;) {
@@ -486,17 +491,23 @@ __device__ __forceinline__ void walk_hit_row(const Dev& d, Ctx& cx, int i, const
 #pragma unroll
       for (int t = 0; t < 4; t++) idx[t] = jj[t];
     }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const unsigned q = pos + (unsigned)t;
-      if ((unsigned)t < nv && q < cap) *reinterpret_cast<uint16_t*>(li + (q >> 2) * rowbytes + (q & 3u) * 2u) = (uint16_t)idx[t];
-    }
-    pos += nv;
+    // invalid slots (t >= nv) hold the dummy N (plain) or its table entry (ghost): XOR N of slot t is forced to 0 there
+    const unsigned n16 = (unsigned)N;
+    const unsigned e0 = idx[0] ^ n16, e1 = nv > 1u ? idx[1] ^ n16 : 0u, e2 = nv > 2u ? idx[2] ^ n16 : 0u, e3 = nv > 3u ? idx[3] ^ n16 : 0u;
+    const unsigned long long packed = (unsigned long long)(e0 | (e1 << 16)) | ((unsigned long long)(e2 | (e3 << 16)) << 32);
+    const unsigned sh = 16u * fill;
+    const unsigned long long lo = acc | (packed << sh);
+    const unsigned long long hi = fill ? packed >> (64u - sh) : 0ull;
+    fill += nv; pos += nv;
+    if (fill >= 4u) {
+      if (oq < (unsigned)d.maxq) *reinterpret_cast<unsigned long long*>(li + oq * rowbytes) = lo ^ dummy4;
+      oq++; acc = hi; fill -= 4u;
+    } else acc = lo;
   }
   tot = (double)pos;
-  if (pos > cap) { over = 1; pos = cap; }
-  for (; pos & 3u; pos++) *reinterpret_cast<uint16_t*>(li + (pos >> 2) * rowbytes + (pos & 3u) * 2u) = (uint16_t)N;   // dummy padding
-  cx.nnb[i] = (uint16_t)(pos >> 2);
+  if (fill) { if (oq < (unsigned)d.maxq) *reinterpret_cast<unsigned long long*>(li + oq * rowbytes) = acc ^ dummy4; oq++; }
+  if (pos > cap) over = 1;
+  cx.nnb[i] = (uint16_t)min(oq, (unsigned)d.maxq);
   const double invL = 1.0 / cx.L;
   cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
 }
