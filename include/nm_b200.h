@@ -78,7 +78,7 @@ enum nm_counter_col {
   NM_CT_CLK_OUTER,         /* SM clocks in outer builds                           */
   NM_CT_CLK_INNER,         /* SM clocks in inner builds                           */
   NM_CT_CLK_VEL,           /* SM clocks in the HMC velocity draw                  */
-  NM_CT_RESERVED,
+  NM_CT_HELPED_EVALS,     /* force evaluations whose upper rows a helper CTA computed (LARGE mode)     */
   NM_CT_DBG_LOOPCLK,       /* diagnostics: clocks thread 0 spent in its own pair loop (first atom)  */
   NM_CT_DBG_LOOPIT         /* diagnostics: quad iterations of that loop                             */
 };

@@ -35,6 +35,9 @@ constexpr int RED_HALF = 32 * 9;           // one block_sum scratch area (K <= 9
 constexpr int RED_DOUBLES = 2 * RED_HALF;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
+constexpr int HELP_STRIDE = 16;          // ints per helper record: [0] helper attached, [1] command sequence number (-1: the chain is finished),
+                                         // [2] last completed command, [3] flags (1 energy / virial, 2 fused kick, 4 per-pair minimum image),
+                                         // [4] list buffer, [6..7] in-cutoff ordered pairs of the helper's rows (force-only commands)
 constexpr int NSMALL = 768;              // largest N handled by the all-pairs hit-matrix build (SMALL mode: one atom per thread)
 // SMALL mode resolves periodic images with GHOST atoms: the shared position array is extended by the shifted copies of
 // the atoms within the list radius of a box face (up to 7 per atom), and the list stores the index of the copy to use.
@@ -87,6 +90,12 @@ struct Dev {
                                            // [1 + nrep] CTAs arrived, [2 + nrep] placement invalid, [3 + nrep + smid] CTAs on SM smid
   int nseg, seg_moves;                     // a cycle is cut into nseg segments of seg_moves moves (the unit of scheduling)
   int place;                               // 1: first ticket of every CTA from the SM-aware placement (placement_rank)
+  // force helpers (LARGE mode, fewer configurations than CTA slots): CTAs without a chain of their own evaluate the
+  // upper half of the force rows of a running chain (see helper_serve)
+  int nhelp;                               // CTAs launched beyond nrep (0: off)
+  int* help;                               // [nrep][HELP_STRIDE] hand-shake record of configuration c (reset by k_schedule)
+  double* helpd;                           // [nrep][4] command parameters: box, dtf
+  double* hpart;                           // [nrep][4][nthr] the helper's per-thread partial sums (energy, virial, pairs, kinetic)
   int list_pf;                             // force loop: prefetch the list row this many rows past the one being loaded into L1 (-1: off)
   int *status;                             // [nrep]
   // per local slot
@@ -135,6 +144,9 @@ struct Ctx {
   size_t list_stride;           // quads per list buffer
   int status;
   int redflip;                  // which half of `red` the next block_sum uses
+  int* help;                    // this configuration's helper record (nullptr: no helpers -- every kernel but k_cycle in LARGE mode)
+  int help_seq;                 // commands issued to the helper so far in this cycle
+  double *helpd, *hpart;
 };
 
 // shared-memory carve (ctx_init): doubles first (positions [+ ghost copies], reduction / broadcast scratch, image shifts,
@@ -155,6 +167,11 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
 }
 
 namespace {   // device functions: internal linkage (this file is compiled as several translation units, see NM_TU)
+
+// gpu-scope acquire load / release store (segment hand-over of the persistent kernel, force helpers). ptxas follows every
+// acquire load with CCTL.IVALL: the SM's L1 is dropped, so plain loads issued after a barrier see the other SM's writes.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 
 // block_sum on alternating scratch halves (see nm_device.cuh): one barrier per reduction
 template <int K>
@@ -226,6 +243,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.mic = d.micmode[c];
   cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.list_pairs = d.list_pairs[c];
   cx.status = 0;
+  cx.help = nullptr; cx.help_seq = 0; cx.helpd = nullptr; cx.hpart = nullptr;
   if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; for (int k = 0; k < NM_COUNTER_WIDTH; k++) cx.ct[k] = 0; }
 }
 
@@ -902,20 +920,15 @@ __device__ __forceinline__ void lj_pair(double xj, double yj, double zj, double 
   fx = fma(dx, fpair, fx); fy = fma(dy, fpair, fy); fz = fma(dz, fpair, fz);
 }
 
-// EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
-// half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
-// Ends with a barrier: shared positions may be rewritten afterwards.
-// IMG: how a list entry names the periodic image of its atom. 0: one image code per quad (LARGE mode), 1: per-pair
-// minimum image (small boxes), 2: the entry is the index of the copy to use (SMALL mode ghost atoms: nothing to do).
+// the force rows [i0, i1) of one evaluation (thread t owns atoms i0 + t, i0 + t + blockDim, ...): forces (and the kicked
+// velocities) go to global memory, the energy / virial / kinetic / pair sums of the rows to the caller's accumulators
 template <bool EW, bool KICK, int IMG, bool S32>
-__device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
+__device__ __forceinline__ void force_rows(const Dev& d, Ctx& cx, double dtf, int i0, int i1, double& e, double& vir, double& ke, int& np) {
   constexpr bool MIC = IMG == 1;
-  const int N = cx.N, Npad = cx.Npad;
+  const int Npad = cx.Npad;
   const long long rc2_bits = __double_as_longlong(d.rc * d.rc);
   const int L_hi = __double2hiint(cx.L), L_lo = __double2loint(cx.L), hL_hi = __double2hiint(0.5 * cx.L);
-  double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
-  const long long t_eval0 = clock64();
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
 #ifdef NM_DEBUG_LOOPCLOCKS
     const long long t_atom0 = clock64();
 #endif
@@ -938,7 +951,11 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       const unsigned a0 = sp_s + 24u * (IMG == 0 ? cur.x & 0x1fffu : cur.x & 0xffffu), a1 = sp_s + 24u * (IMG == 0 ? (cur.x >> 16) & 0x1fffu : cur.x >> 16),
                      a2 = sp_s + 24u * (cur.y & 0xffffu), a3 = sp_s + 24u * (cur.y >> 16);
       double p[12];
-#ifdef NM_PLAIN_GATHER
+#ifdef NM_FAKE_GATHER   // timing experiment only (wrong physics): conflict-free gathers, same instruction stream
+      { const unsigned fk = 24u * ((threadIdx.x + (cur.x & 63u)) & 511u);
+        lds_f64x3(sp_s + fk + (a0 & 0u), p[0], p[1], p[2]); lds_f64x3(sp_s + fk + 24u + (a1 & 0u), p[3], p[4], p[5]);
+        lds_f64x3(sp_s + fk + 48u + (a2 & 0u), p[6], p[7], p[8]); lds_f64x3(sp_s + fk + 72u + (a3 & 0u), p[9], p[10], p[11]); }
+#elif defined(NM_PLAIN_GATHER)
       { const double *q0 = cx.sp + (a0 - sp_s) / 8u, *q1 = cx.sp + (a1 - sp_s) / 8u, *q2 = cx.sp + (a2 - sp_s) / 8u, *q3 = cx.sp + (a3 - sp_s) / 8u;
         p[0] = q0[0]; p[1] = q0[1]; p[2] = q0[2]; p[3] = q1[0]; p[4] = q1[1]; p[5] = q1[2];
         p[6] = q2[0]; p[7] = q2[1]; p[8] = q2[2]; p[9] = q3[0]; p[10] = q3[1]; p[11] = q3[2]; }
@@ -997,8 +1014,75 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       if (EW) ke += vx * vx + vy * vy + vz * vz;
     }
   }
+}
+
+// ---- force helpers (LARGE mode). With fewer configurations than SMs (C3: 128 chains on 148 SMs) the spare CTAs of the
+// grid, and every CTA whose own chain has finished, attach themselves to a running chain (most expensive first) and
+// evaluate the force rows [2 * blockDim, N) of each of its evaluations while the owner does rows [0, 2 * blockDim): the
+// owner publishes its positions (shared -> global x) and a command (release), the helper gathers them into its own
+// shared memory, walks the same list rows with the same arithmetic, writes f (and the kicked v) of its atoms and its
+// per-thread partial sums, and answers (release). The owner never waits for a helper that has not announced itself, so
+// no CTA depends on another one being resident. Results do not depend on whether, when or by whom a chain is helped:
+// per-atom forces are independent, and the energy / virial / kinetic sums are formed as (rows below the split) +
+// (rows above it) per thread in either case.
+__device__ __forceinline__ bool help_request(Ctx& cx, int flags, double dtf) {
+  if (threadIdx.x == 0) cx.ibc[4] = ld_acquire_gpu(cx.help);
+  __syncthreads();
+  if (cx.ibc[4] != 1) return false;
+  store_positions(cx);
+  cx.help_seq++;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cx.help[3] = flags; cx.help[4] = cx.lbuf;
+    cx.helpd[0] = cx.L; cx.helpd[1] = dtf;
+    st_release_gpu(cx.help + 1, cx.help_seq);
+  }
+  return true;
+}
+// wait for the helper's answer; the barrier that follows the acquire (and its L1 invalidation) publishes it to the CTA
+__device__ __forceinline__ void help_wait(Ctx& cx) {
+  if (threadIdx.x == 0) while (ld_acquire_gpu(cx.help + 2) != cx.help_seq) __nanosleep(64);
+  __syncthreads();
+}
+
+// EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
+// half kick v += dtf*f of the owning thread, KE returned in out[3] when EW.
+// Ends with a barrier: shared positions may be rewritten afterwards.
+// IMG: how a list entry names the periodic image of its atom. 0: one image code per quad (LARGE mode), 1: per-pair
+// minimum image (small boxes), 2: the entry is the index of the copy to use (SMALL mode ghost atoms: nothing to do).
+template <bool EW, bool KICK, int IMG, bool S32>
+__device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4]) {
+  const int N = cx.N;
+  const long long t_eval0 = clock64();
+  double e = 0.0, vir = 0.0, ke = 0.0, e1 = 0.0, vir1 = 0.0, ke1 = 0.0, np1 = 0.0; int np = 0;
+  bool assisted = false;
+  if (S32 && IMG != 2) {
+    // rows above the split are summed separately (see the helper note above); the split depends on N alone
+    const int Ns = (!d.small && N > 2 * (int)blockDim.x) ? 2 * (int)blockDim.x : N;
+    if (Ns < N && cx.help) assisted = help_request(cx, (EW ? 1 : 0) | (KICK ? 2 : 0) | (IMG == 1 ? 4 : 0), dtf);
+    const int nparts = (Ns < N && !assisted) ? 2 : 1;
+#pragma unroll 1
+    for (int part = 0; part < nparts; part++) {
+      double pe = 0.0, pv = 0.0, pk = 0.0;
+      force_rows<EW, KICK, IMG, S32>(d, cx, dtf, part ? Ns : 0, part ? N : Ns, pe, pv, pk, np);
+      if (part == 0) { e = pe; vir = pv; ke = pk; } else { e1 = pe; vir1 = pv; ke1 = pk; }
+    }
+    if (assisted) {
+      help_wait(cx);
+#if !defined(NM_DEBUG_CLOCKS) && !defined(NM_DEBUG_SMID)     // (the debug builds keep other figures in this column)
+      if (threadIdx.x == 0) cx.ct[NM_CT_HELPED_EVALS]++;
+#endif
+      if (EW) {
+        const int nt = (int)blockDim.x, t = (int)threadIdx.x;
+        e1 = cx.hpart[t]; vir1 = cx.hpart[nt + t]; np1 = cx.hpart[2 * nt + t]; ke1 = cx.hpart[3 * nt + t];
+      } else if (threadIdx.x == 0) atomicAdd(cx.s_pairs, *reinterpret_cast<const unsigned long long*>(cx.help + 6));
+    }
+  } else {
+    force_rows<EW, KICK, IMG, S32>(d, cx, dtf, 0, N, e, vir, ke, np);
+  }
   if (EW) {
-    double r[4] = { 0.5 * e, 0.5 * vir, (double)np, ke };
+    double r[4] = { 0.5 * (e + e1), 0.5 * (vir + vir1), (double)np + np1, ke + ke1 };
     bsum<4>(r, cx);
     out[0] = r[0]; out[1] = r[1]; out[2] = 0.5 * r[2]; out[3] = 0.5 * d.mass * r[3];
     if (threadIdx.x == 0) {
@@ -1653,7 +1737,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
     __syncthreads();
 #ifdef NM_DEBUG_CLOCKS
     const long long t_round1 = clk_fenced();
-    if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(t_round1 - t_round0); cx.ct[NM_CT_RESERVED]++; }
+    if (threadIdx.x == 0) { cx.ct[NM_CT_DBG_LOOPCLK] += (unsigned long long)(t_round1 - t_round0); cx.ct[NM_CT_HELPED_EVALS]++; }
 #endif
     // ---- (C) ordered commit: lane l holds the running dE of trial k + l
     if (wid == 0) {
@@ -1734,8 +1818,57 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
 // cheapest unfinished chain, so every SM stays busy to the end of the cycle. The state that crosses a segment boundary is
 // exactly the state that crosses a cycle boundary (positions, box, energies, step counters, list bookkeeping, all in
 // global memory), so results are bit-identical to the unsegmented cycle and independent of the schedule.
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+// A CTA without a chain of its own serves configuration c until that chain is finished (see the note at help_request).
+template <int NTHR>
+__device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
+  Ctx cx; ctx_init(d, cx, c, smem);
+  int* hs = d.help + (size_t)HELP_STRIDE * c;
+  const double* hd = d.helpd + 4 * (size_t)c;
+  double* hp = d.hpart + (size_t)c * 4 * NTHR;
+  const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, Ns = 2 * NTHR;
+  for (int i = N + tid; i < Npad; i += NTHR) { cx.sp[3 * i] = 1e9; cx.sp[3 * i + 1] = 1e9; cx.sp[3 * i + 2] = 1e9; }
+  __syncthreads();
+  if (tid == 0) st_release_gpu(hs, 1);                   // attached: the owner may send commands from now on
+  for (int seq = 1;; seq++) {
+    if (tid == 0) {
+      int v;
+      while ((v = ld_acquire_gpu(hs + 1)) != seq && v != -1) __nanosleep(128);
+      cx.ibc[5] = v;
+    }
+    __syncthreads();
+    if (cx.ibc[5] == -1) break;
+    const int flags = hs[3];
+    cx.lbuf = hs[4]; select_list(cx);
+    cx.L = hd[0]; cx.mic = (flags >> 2) & 1;
+    const double dtf = hd[1];
+    if (tid < 27) { cx.sht[3 * tid] = (tid / 9 - 1) * cx.L; cx.sht[3 * tid + 1] = ((tid / 3) % 3 - 1) * cx.L; cx.sht[3 * tid + 2] = (tid % 3 - 1) * cx.L; }
+    for (int i = tid; i < N; i += NTHR) { cx.sp[3 * i] = __ldcg(cx.gx + i); cx.sp[3 * i + 1] = __ldcg(cx.gx + Npad + i); cx.sp[3 * i + 2] = __ldcg(cx.gx + 2 * Npad + i); }
+    if (tid == 0) cx.s_pairs[0] = 0ull;
+    __syncthreads();
+    double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
+    switch (flags & 7) {
+      case 1: force_rows<true, false, 0, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
+      case 2: force_rows<false, true, 0, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
+      case 3: force_rows<true, true, 0, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
+      case 5: force_rows<true, false, 1, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
+      case 6: force_rows<false, true, 1, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
+      case 7: force_rows<true, true, 1, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
+      default: break;
+    }
+    if (flags & 1) { hp[tid] = e; hp[NTHR + tid] = vir; hp[2 * NTHR + tid] = (double)np; hp[3 * NTHR + tid] = ke; }
+    else {
+      np = __reduce_add_sync(0xffffffffu, np);
+      if ((tid & 31) == 0) atomicAdd(cx.s_pairs, (unsigned long long)np);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      if (!(flags & 1)) *reinterpret_cast<unsigned long long*>(hs + 6) = cx.s_pairs[0];
+      st_release_gpu(hs + 2, seq);
+    }
+  }
+}
 
 // SM-aware placement (thread 0 of every CTA, once per launch; nsm < nrep <= 2 nsm, two CTAs fit per SM, whole grid resident).
 // The block scheduler deals the CTAs breadth-first: 2 nsm - nrep SMs end up with ONE CTA, which then runs ~1.4x faster than a
@@ -1779,13 +1912,29 @@ k_cycle(Dev d, long long cycle) {
     first = false;
     __syncthreads();
     const int ticket = s_ticket;
-    if (ticket >= ntickets) break;
+    if (ticket >= ntickets) {
+      // no chain left: help the running chains, most expensive first (every chain is claimed by at most one helper)
+      if constexpr (NTHR == 1024) for (; d.nhelp > 0;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int h, c = -1;
+          while ((h = atomicAdd(&d.sched[3 + d.nrep + SMID_MAX], 1)) < d.nrep) { c = d.order[h]; if (ld_acquire_gpu(d.help + (size_t)HELP_STRIDE * c + 1) != -1) break; c = -1; }
+          s_ticket = c;
+        }
+        __syncthreads();
+        const int c = s_ticket;
+        if (c < 0) break;
+        helper_serve<NTHR>(d, smem, c);
+      }
+      break;
+    }
     const int seg = ticket / d.nrep, c = d.order[ticket - seg * d.nrep];
     if (seg > 0) {
       if (threadIdx.x == 0) while (ld_acquire_gpu(&d.sched[1 + c]) < seg) __nanosleep(256);
       __syncthreads();
     }
     Ctx cx; ctx_init(d, cx, c, smem);
+    if (NTHR == 1024 && d.nhelp > 0) { cx.help = d.help + (size_t)HELP_STRIDE * c; cx.helpd = d.helpd + 4 * (size_t)c; cx.hpart = d.hpart + (size_t)c * 4 * NTHR; }
     const int slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
     const long long t_seg0 = clock64();
     const double et = d.label[4 * slot], pf = d.label[4 * slot + 1], t_vel = d.label[4 * slot + 3];
@@ -1839,14 +1988,18 @@ k_cycle(Dev d, long long cycle) {
       if (cx.status) d.status[c] |= cx.status;
       cx.ct[NM_CT_PAIRS_FORCE] += cx.s_pairs[0] / 2;
 #ifdef NM_DEBUG_SMID
-      { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); cx.ct[NM_CT_RESERVED] = smid; }
+      { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); cx.ct[NM_CT_HELPED_EVALS] = smid; }
 #endif
       const unsigned long long dt_seg = (unsigned long long)(clock64() - t_seg0);
       cx.ct[NM_CT_CLK_TOTAL] += dt_seg;
       // per-configuration bookkeeping of the cycle (cost ranks for the next schedule, diagnostics): reset by segment 0
       const unsigned long long old_cnt = seg ? d.mv_clk[4 * c + 3] : 0ull;
       d.cta_clk[c] = (seg ? d.cta_clk[c] : 0ull) + dt_seg;
-      d.cost[2 * c] = (seg ? d.cost[2 * c] : 0ull) + cx.ct[NM_CT_LIST_PAIRS] + cx.ct[NM_CT_LIST_BUILDS] * (unsigned long long)(0.3 * N * N);
+      // work estimate in units of one listed pair: evaluations + list builds (SMALL: all-pairs tiles + row walk; LARGE, measured
+      // at N = 4000: an inner build ~ 75 N, an outer build ~ 650 N pair evaluations)
+      d.cost[2 * c] = (seg ? d.cost[2 * c] : 0ull) + cx.ct[NM_CT_LIST_PAIRS] +
+                      (d.small ? cx.ct[NM_CT_LIST_BUILDS] * (unsigned long long)(0.3 * N * N)
+                               : (cx.ct[NM_CT_LIST_BUILDS] * 75ull + cx.ct[NM_CT_OUTER_BUILDS] * 650ull) * (unsigned long long)N);
       d.cost[2 * c + 1] = (seg ? d.cost[2 * c + 1] : 0ull) + cx.ct[NM_CT_FORCE_EVALS];
       for (int k = 0; k < 3; k++) d.mv_clk[4 * c + k] = (seg ? d.mv_clk[4 * c + k] : 0ull) + kclk[k];
       unsigned long long packed = 0ull;
@@ -1859,7 +2012,10 @@ k_cycle(Dev d, long long cycle) {
     }
     __threadfence();                                    // this thread's state writes are visible device-wide ...
     __syncthreads();                                    // ... for every thread of the CTA, before thread 0 publishes the segment
-    if (threadIdx.x == 0) st_release_gpu(&d.sched[1 + c], seg + 1);
+    if (threadIdx.x == 0) {
+      st_release_gpu(&d.sched[1 + c], seg + 1);
+      if (cx.help) st_release_gpu(cx.help + 1, -1);       // dismiss the helper (or whoever claims this chain later)
+    }
   }
 }
 
@@ -1921,14 +2077,15 @@ NM_LAUNCHERS(1024)
 __global__ void k_schedule(Dev d, long long cycle, int do_sort) {
   extern __shared__ unsigned long long sclk[];
   int* sorted = reinterpret_cast<int*>(sclk + d.nrep);
-  for (int c = threadIdx.x; c < 3 + d.nrep + SMID_MAX; c += blockDim.x) d.sched[c] = (c == 0 && d.place) ? d.nrep : 0;   // placement hands out the first nrep tickets
+  for (int c = threadIdx.x; c < 4 + d.nrep + SMID_MAX; c += blockDim.x) d.sched[c] = (c == 0 && d.place) ? d.nrep : 0;   // placement hands out the first nrep tickets
+  if (d.nhelp > 0) for (int c = threadIdx.x; c < HELP_STRIDE * d.nrep; c += blockDim.x) d.help[c] = 0;
   if (!do_sort) { for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) d.order[c] = c; return; }
   // predicted cost of the coming cycle: last cycle's work estimate of the configuration (listed pairs evaluated + list builds:
   // independent of which SM it ran on and with whom), scaled by the number of force evaluations the coming cycle will make
   // -- the move kinds are known in advance (counter-based RNG: the same rolls k_cycle will draw)
   for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) {
     unsigned long long cost = d.cost[2 * c];
-    const unsigned long long evals_last = d.cost[2 * c + 1];
+    const unsigned long long evals_last = d.nhelp > 0 ? 0ull : d.cost[2 * c + 1];     // helper ranks: last cycle's work as it is
     if (evals_last) {
       unsigned long long evals = 0;
       const int slot = d.cfg_slot[c];
@@ -2179,7 +2336,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
-  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.cost, 2 * (size_t)nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep); DA(d.sched, (size_t)nrep + 3 + SMID_MAX);
+  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.cost, 2 * (size_t)nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep); DA(d.sched, (size_t)nrep + 4 + SMID_MAX);
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
@@ -2221,6 +2378,19 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     if (const char* ev = getenv("NM_LIST_PF")) d.list_pf = atoi(ev);
     if (d.list_pf > LIST_SPARE_ROWS - 2) d.list_pf = LIST_SPARE_ROWS - 2;      // stays inside the spare rows of the list buffer
     d.place = occ == 2 && nrep > h->nsm && nrep <= slots && h->nsm <= SMID_MAX && !getenv("NM_NO_PLACEMENT");
+    // force helpers: LARGE mode with rows above 2 * blockDim, one segment per cycle, spare CTA slots (NM_NO_HELPERS: off;
+    // NM_HELPERS=n: at most n). The grid grows by the helpers; all of it fits the device at once.
+    d.nhelp = 0;
+    if (!d.small && !d.f32 && h->threads == 1024 && N > 2 * h->threads && d.nseg == 1 && nrep < slots && !getenv("NM_NO_HELPERS")) {
+      long long nh = slots - nrep;
+      if (nh > nrep) nh = nrep;
+      if (const char* ev = getenv("NM_HELPERS")) { const long long lim = atoll(ev); if (lim >= 0 && lim < nh) nh = lim; }
+      d.nhelp = (int)nh;
+    }
+    if (d.nhelp > 0) {
+      DA(d.help, (size_t)HELP_STRIDE * nrep); DA(d.helpd, 4 * (size_t)nrep); DA(d.hpart, (size_t)nrep * 4 * h->threads);
+      h->grid += d.nhelp;
+    }
   }
   *out = h;
   return NM_OK;
@@ -2344,7 +2514,7 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   if (!h->have_state || !h->have_labels) return fail(NM_ESTATE, "nm_run_cycle: state and labels must be uploaded first");
   CK(cudaSetDevice(h->cfg.device));
   {                                                       // queue reset + cost ranks from the last cycle's clocks and this cycle's move kinds
-    const int do_sort = h->d.nrep > 1 && h->d.nrep <= 4096 && (h->d.nseg > 1 || h->d.nrep > h->nsm);
+    const int do_sort = h->d.nrep > 1 && h->d.nrep <= 4096 && (h->d.nseg > 1 || h->d.nrep > h->nsm || h->d.nhelp > 0);
     k_schedule<<<1, 1024, do_sort ? h->d.nrep * (sizeof(unsigned long long) + sizeof(int)) : 0, h->stream>>>(h->d, (long long)cycle, do_sort);
     h->launches++;
     CK(cudaGetLastError());

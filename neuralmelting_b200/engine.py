@@ -19,7 +19,7 @@ THERMO_COLS = ("temp", "pe", "ke", "virial", "box", "vol", "dx", "dv", "dt",
 COUNTER_WIDTH = 22
 COUNTER_COLS = ("sweeps", "hmc_moves", "hmc_atom_steps", "vmc_moves", "pmc_moves", "pmc_trials",
                 "force_evals", "pairs_force", "pairs_full", "pairs_delta", "list_builds", "list_pairs",
-                "clk_eval", "clk_build", "clk_total", "outer_builds", "clk_outer", "clk_inner", "clk_vel", "reserved", "dbg_loopclk", "dbg_loopit")
+                "clk_eval", "clk_build", "clk_total", "outer_builds", "clk_outer", "clk_inner", "clk_vel", "helped_evals", "dbg_loopclk", "dbg_loopit")
 
 NM_OK, NM_EINVAL, NM_ENODEV, NM_ECUDA, NM_ENOMEM, NM_EBOX, NM_ENEIGH, NM_ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 

@@ -52,7 +52,7 @@ def main():
         print("   per-call clk: outer %.0f inner %.0f vel %.0f | share outer %.2f inner %.2f vel %.2f" % (ct["clk_outer"] / max(1, ct["outer_builds"] or ct["list_builds"]), ct["clk_inner"] / max(1, ct["list_builds"]), ct["clk_vel"] / max(1, ct["hmc_moves"]), ct["clk_outer"] / ct["clk_total"], ct["clk_inner"] / ct["clk_total"], ct["clk_vel"] / ct["clk_total"]))
         print("   build phases (debug build): tiles %.0f  tiles+ghost table %.0f  row walk %.0f  clk per build" % (ct["clk_outer"] / max(1, ct["list_builds"]), ct["dbg_loopit"] / max(1, ct["list_builds"]), ct["dbg_loopclk"] / max(1, ct["list_builds"])))
         if not bulk:
-            print("   iterative PMC (debug build): rounds %d  trials/round %.1f  clk/round: evaluate %.0f commit %.0f  acc %.2f  (of the evaluate: proposals %.0f)" % (ct["reserved"], ct["pmc_trials"] / max(1, ct["reserved"]), ct["dbg_loopclk"] / max(1, ct["reserved"]), ct["dbg_loopit"] / max(1, ct["reserved"]), th[:, 15].mean(), ct["clk_vel"] / max(1, ct["reserved"])))
+            print("   iterative PMC (debug build): rounds %d  trials/round %.1f  clk/round: evaluate %.0f commit %.0f  acc %.2f  (of the evaluate: proposals %.0f)" % (ct["helped_evals"], ct["pmc_trials"] / max(1, ct["helped_evals"]), ct["dbg_loopclk"] / max(1, ct["helped_evals"]), ct["dbg_loopit"] / max(1, ct["helped_evals"]), th[:, 15].mean(), ct["clk_vel"] / max(1, ct["helped_evals"])))
         print("   outer builds %d | clk share: eval %.2f build %.2f  | clk/eval %.0f clk/build %.0f  | total Mclk/CTA %.1f" % (ct["outer_builds"], ct["clk_eval"] / ct["clk_total"], ct["clk_build"] / ct["clk_total"], ct["clk_eval"] / max(1, ct["force_evals"]), ct["clk_build"] / max(1, ct["list_builds"]), ct["clk_total"] / ns / 1e6))
     clk = eng.cta_clocks().astype(float).reshape(np_, nt) / 1e6
     print("per-slot Mclk by temperature (mean over P):", np.round(clk.mean(0), 1))
@@ -65,7 +65,7 @@ def main():
         print("%4d  %.2f  %.3f  %5.1f  %4d %4d  %4d  %5d   %6.1f  %6.1f   %7.0f" % (k, tt[k], n / th[k, 5], r[ci["clk_total"]] / 1e6, r[ci["sweeps"]], r[ci["hmc_moves"]],
               r[ci["list_builds"]], r[ci["force_evals"]], r[ci["clk_build"]] / 1e6, r[ci["clk_eval"]] / 1e6, r[ci["list_pairs"]] / max(1, r[ci["force_evals"]])))
     if os.environ.get("SMID"):
-        smid = rc[:, ci["reserved"]].astype(int)
+        smid = rc[:, ci["helped_evals"]].astype(int)
         cnt = np.bincount(smid, minlength=160)
         print("CTAs per SM histogram:", np.bincount(cnt[:int(smid.max()) + 1]), " distinct SMs:", (cnt > 0).sum(), " max smid:", smid.max())
         clkm = rc[:, ci["clk_total"]] / 1e6
