@@ -217,11 +217,13 @@ def measure_mc(args, comm, torch, workload, steps, warmup, equil, with_e2e=True,
         rc = eng.replica_counters().astype(float); ci = {k: i for i, k in enumerate(nm.COUNTER_COLS)}
         th = eng.get_thermo()
         order = np.argsort(-rc[:, ci["clk_total"]])
-        print("slot  T  rho  Mclk  builds outer evals  listed/eval", file=sys.stderr)
+        print("slot  T  rho  Mclk  builds outer evals helped  listed/eval  kclk/eval  Mclk_build", file=sys.stderr)
         for k in order:
             r = rc[k]
-            print("%4d %.2f %.3f %6.1f %4d %3d %4d %7.0f" % (k, th[k, 0], natoms / th[k, 5], r[ci["clk_total"]] / 1e6, r[ci["list_builds"]], r[ci["outer_builds"]],
-                                                            r[ci["force_evals"]], r[ci["list_pairs"]] / max(1, r[ci["force_evals"]])), file=sys.stderr)
+            print("%4d %.2f %.3f %6.1f %4d %3d %4d %4d %7.0f %6.1f %6.1f" % (k, th[k, 0], natoms / th[k, 5], r[ci["clk_total"]] / 1e6, r[ci["list_builds"]], r[ci["outer_builds"]],
+                  r[ci["force_evals"]], r[ci["helped_evals"]], r[ci["list_pairs"]] / max(1, r[ci["force_evals"]]), r[ci["clk_eval"]] / max(1, r[ci["force_evals"]]) / 1e3,
+                  r[ci["clk_build"]] / 1e6), file=sys.stderr)
+        print("sum of chain Mclk %.0f  / nsm(148) = %.1f" % (rc[:, ci["clk_total"]].sum() / 1e6, rc[:, ci["clk_total"]].sum() / 1e6 / 148), file=sys.stderr)
     gate = parity_gate(eng, natoms, nloc) if (with_gate and comm.rank == 0 and args.precision == 64) else None
     # ---------------- end-to-end through the public API with HOST buffers (pinned): state in, cycle, state + thermo out
     e2e_ms, atom_steps_e2e_local, sweeps_e2e_local, e2e_steps = 0.0, 0.0, 0.0, 0

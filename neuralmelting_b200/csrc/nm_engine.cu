@@ -35,9 +35,10 @@ constexpr int RED_HALF = 32 * 9;           // one block_sum scratch area (K <= 9
 constexpr int RED_DOUBLES = 2 * RED_HALF;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
-constexpr int HELP_STRIDE = 16;          // ints per helper record: [0] helper attached, [1] command sequence number (-1: the chain is finished),
-                                         // [2] last completed command, [3] flags (1 energy / virial, 2 fused kick, 4 per-pair minimum image),
-                                         // [4] list buffer, [6..7] in-cutoff ordered pairs of the helper's rows (force-only commands)
+constexpr int HELP_STRIDE = 16;          // ints per helper record: [0] helper attached, [1] last command issued (-1: the chain is finished),
+                                         // [2] last command completed, [3] flags (1 energy / virial, 2 fused kick, 4 per-pair minimum image),
+                                         // [4] list buffer, [5] claimed by a helper, [6..7] in-cutoff ordered pairs of the helper's rows
+                                         // (force-only commands), [8] the owner's estimate of its remaining clocks / 1024
 constexpr int NSMALL = 768;              // largest N handled by the all-pairs hit-matrix build (SMALL mode: one atom per thread)
 // SMALL mode resolves periodic images with GHOST atoms: the shared position array is extended by the shifted copies of
 // the atoms within the list radius of a box face (up to 7 per atom), and the list stores the index of the copy to use.
@@ -93,6 +94,7 @@ struct Dev {
   // force helpers (LARGE mode, fewer configurations than CTA slots): CTAs without a chain of their own evaluate the
   // upper half of the force rows of a running chain (see helper_serve)
   int nhelp;                               // CTAs launched beyond nrep (0: off)
+  int help_quantum;                        // commands a helper serves before it looks for the chain that needs help most
   int* help;                               // [nrep][HELP_STRIDE] hand-shake record of configuration c (reset by k_schedule)
   double* helpd;                           // [nrep][4] command parameters: box, dtf
   double* hpart;                           // [nrep][4][nthr] the helper's per-thread partial sums (energy, virial, pairs, kinetic)
@@ -1017,14 +1019,16 @@ __device__ __forceinline__ void force_rows(const Dev& d, Ctx& cx, double dtf, in
 }
 
 // ---- force helpers (LARGE mode). With fewer configurations than SMs (C3: 128 chains on 148 SMs) the spare CTAs of the
-// grid, and every CTA whose own chain has finished, attach themselves to a running chain (most expensive first) and
-// evaluate the force rows [2 * blockDim, N) of each of its evaluations while the owner does rows [0, 2 * blockDim): the
-// owner publishes its positions (shared -> global x) and a command (release), the helper gathers them into its own
-// shared memory, walks the same list rows with the same arithmetic, writes f (and the kicked v) of its atoms and its
-// per-thread partial sums, and answers (release). The owner never waits for a helper that has not announced itself, so
-// no CTA depends on another one being resident. Results do not depend on whether, when or by whom a chain is helped:
-// per-atom forces are independent, and the energy / virial / kinetic sums are formed as (rows below the split) +
-// (rows above it) per thread in either case.
+// grid, and every CTA whose own chain has finished, attach themselves to the running chain with the most work left (the
+// owners publish an estimate after every move) and evaluate the force rows [2 * blockDim, N) of its evaluations while the
+// owner does rows [0, 2 * blockDim): the owner publishes its positions (shared -> global x) and a command (release), the
+// helper gathers them into its own shared memory, walks the same list rows with the same arithmetic, writes f (and the
+// kicked v) of its atoms and its per-thread partial sums, and answers (release). After help_quantum commands the helper
+// detaches (it clears the attached flag BEFORE its last answer, so the owner cannot address it again) and chooses anew:
+// helped chains fall back in the ranking, and all chains finish at about the same time. The owner never waits for a
+// helper that has not announced itself, so no CTA depends on another one being resident. Results do not depend on
+// whether, when or by whom a chain is helped: per-atom forces are independent, and the energy / virial / kinetic sums
+// are formed as (rows below the split) + (rows above it) per thread in either case.
 __device__ __forceinline__ bool help_request(Ctx& cx, int flags, double dtf) {
   if (threadIdx.x == 0) cx.ibc[4] = ld_acquire_gpu(cx.help);
   __syncthreads();
@@ -1819,7 +1823,8 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
 // exactly the state that crosses a cycle boundary (positions, box, energies, step counters, list bookkeeping, all in
 // global memory), so results are bit-identical to the unsegmented cycle and independent of the schedule.
 
-// A CTA without a chain of its own serves configuration c until that chain is finished (see the note at help_request).
+// A CTA without a chain of its own serves configuration c (which it has claimed) for up to help_quantum commands or
+// until that chain is finished (see the note at help_request).
 template <int NTHR>
 __device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
   Ctx cx; ctx_init(d, cx, c, smem);
@@ -1828,16 +1833,21 @@ __device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
   double* hp = d.hpart + (size_t)c * 4 * NTHR;
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, Ns = 2 * NTHR;
   for (int i = N + tid; i < Npad; i += NTHR) { cx.sp[3 * i] = 1e9; cx.sp[3 * i + 1] = 1e9; cx.sp[3 * i + 2] = 1e9; }
+  if (tid == 0) cx.ibc[5] = ld_acquire_gpu(hs + 1);      // every command up to this one is complete (the claim is exclusive)
+  __syncthreads();
+  int seq = cx.ibc[5];
+  if (seq == -1) return;                                 // finished in the meantime (the claim stays: nobody needs it)
   __syncthreads();
   if (tid == 0) st_release_gpu(hs, 1);                   // attached: the owner may send commands from now on
-  for (int seq = 1;; seq++) {
+  for (int served = 1;; served++) {
+    seq++;
     if (tid == 0) {
       int v;
       while ((v = ld_acquire_gpu(hs + 1)) != seq && v != -1) __nanosleep(128);
       cx.ibc[5] = v;
     }
     __syncthreads();
-    if (cx.ibc[5] == -1) break;
+    if (cx.ibc[5] == -1) return;
     const int flags = hs[3];
     cx.lbuf = hs[4]; select_list(cx);
     cx.L = hd[0]; cx.mic = (flags >> 2) & 1;
@@ -1861,12 +1871,16 @@ __device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
       np = __reduce_add_sync(0xffffffffu, np);
       if ((tid & 31) == 0) atomicAdd(cx.s_pairs, (unsigned long long)np);
     }
+    const bool leave = served >= d.help_quantum;
     __threadfence();
     __syncthreads();
     if (tid == 0) {
       if (!(flags & 1)) *reinterpret_cast<unsigned long long*>(hs + 6) = cx.s_pairs[0];
+      if (leave) st_release_gpu(hs, 0);                  // detached before the answer: the owner will not address this CTA again
       st_release_gpu(hs + 2, seq);
+      if (leave) st_release_gpu(hs + 5, 0);              // the chain may be claimed again
     }
+    if (leave) return;
   }
 }
 
@@ -1913,12 +1927,21 @@ k_cycle(Dev d, long long cycle) {
     __syncthreads();
     const int ticket = s_ticket;
     if (ticket >= ntickets) {
-      // no chain left: help the running chains, most expensive first (every chain is claimed by at most one helper)
+      // no chain left: help the running chain with the most work left (claims are exclusive), until every chain is finished
       if constexpr (NTHR == 1024) for (; d.nhelp > 0;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-          int h, c = -1;
-          while ((h = atomicAdd(&d.sched[3 + d.nrep + SMID_MAX], 1)) < d.nrep) { c = d.order[h]; if (ld_acquire_gpu(d.help + (size_t)HELP_STRIDE * c + 1) != -1) break; c = -1; }
+          int c = -1;
+          const int* finished = d.sched + 3 + d.nrep + SMID_MAX;
+          while (ld_acquire_gpu(finished) < d.nrep) {
+            int best = -1, bestrem = 0;
+            for (int o = 0; o < d.nrep; o++) {
+              const volatile int* r = d.help + (size_t)HELP_STRIDE * o;
+              if (r[5] == 0 && r[1] != -1) { const int rem = r[8]; if (rem > bestrem) { bestrem = rem; best = o; } }
+            }
+            if (best < 0) { __nanosleep(2000); continue; }
+            if (atomicCAS(d.help + (size_t)HELP_STRIDE * best + 5, 0, 1) == 0) { c = best; break; }
+          }
           s_ticket = c;
         }
         __syncthreads();
@@ -1957,7 +1980,14 @@ k_cycle(Dev d, long long cycle) {
         else iter_position_mc<S32>(d, cx, r, et, dxs, en, cnt);
       } else if (kind == 1) volume_mc<S32>(d, cx, r, et, pf, dvs, en, cnt);
       else hamiltonian_mc<S32>(d, cx, r, et, t_vel, dts, en, cnt);
-      if (threadIdx.x == 0) { cx.ct[NM_CT_SWEEPS]++; kclk[kind] += (unsigned long long)(clock64() - t_mv0); kcnt[kind]++; }
+      if (threadIdx.x == 0) {
+        const long long t_now = clock64();
+        cx.ct[NM_CT_SWEEPS]++; kclk[kind] += (unsigned long long)(t_now - t_mv0); kcnt[kind]++;
+        if (cx.help) {                                   // remaining clocks at the pace so far (helpers rank the chains by it)
+          const long long rem = (t_now - t_seg0) / (mv - mv0 + 1) * (mv1 - mv - 1);
+          *reinterpret_cast<volatile int*>(cx.help + 8) = (int)min(rem >> 10, 0x7fffffffll);
+        }
+      }
     }
     const bool last = seg == d.nseg - 1;
     double t[1] = { 0 };
@@ -2014,7 +2044,7 @@ k_cycle(Dev d, long long cycle) {
     __syncthreads();                                    // ... for every thread of the CTA, before thread 0 publishes the segment
     if (threadIdx.x == 0) {
       st_release_gpu(&d.sched[1 + c], seg + 1);
-      if (cx.help) st_release_gpu(cx.help + 1, -1);       // dismiss the helper (or whoever claims this chain later)
+      if (cx.help) { st_release_gpu(cx.help + 1, -1); atomicAdd(d.sched + 3 + d.nrep + SMID_MAX, 1); }   // dismiss the helper; one chain fewer to help
     }
   }
 }
@@ -2078,14 +2108,15 @@ __global__ void k_schedule(Dev d, long long cycle, int do_sort) {
   extern __shared__ unsigned long long sclk[];
   int* sorted = reinterpret_cast<int*>(sclk + d.nrep);
   for (int c = threadIdx.x; c < 4 + d.nrep + SMID_MAX; c += blockDim.x) d.sched[c] = (c == 0 && d.place) ? d.nrep : 0;   // placement hands out the first nrep tickets
-  if (d.nhelp > 0) for (int c = threadIdx.x; c < HELP_STRIDE * d.nrep; c += blockDim.x) d.help[c] = 0;
+  if (d.nhelp > 0) for (int c = threadIdx.x; c < HELP_STRIDE * d.nrep; c += blockDim.x)      // helper records; first ranking: last cycle's clocks
+    d.help[c] = (c % HELP_STRIDE) == 8 ? (int)min((d.cta_clk[c / HELP_STRIDE] >> 10) + 1ull, 0x7fffffffull) : 0;
   if (!do_sort) { for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) d.order[c] = c; return; }
   // predicted cost of the coming cycle: last cycle's work estimate of the configuration (listed pairs evaluated + list builds:
   // independent of which SM it ran on and with whom), scaled by the number of force evaluations the coming cycle will make
   // -- the move kinds are known in advance (counter-based RNG: the same rolls k_cycle will draw)
   for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) {
     unsigned long long cost = d.cost[2 * c];
-    const unsigned long long evals_last = d.nhelp > 0 ? 0ull : d.cost[2 * c + 1];     // helper ranks: last cycle's work as it is
+    const unsigned long long evals_last = d.cost[2 * c + 1];
     if (evals_last) {
       unsigned long long evals = 0;
       const int slot = d.cfg_slot[c];
@@ -2387,6 +2418,8 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
       if (const char* ev = getenv("NM_HELPERS")) { const long long lim = atoll(ev); if (lim >= 0 && lim < nh) nh = lim; }
       d.nhelp = (int)nh;
     }
+    d.help_quantum = 32;
+    if (const char* ev = getenv("NM_HELP_QUANTUM")) { const int q = atoi(ev); if (q > 0) d.help_quantum = q; }
     if (d.nhelp > 0) {
       DA(d.help, (size_t)HELP_STRIDE * nrep); DA(d.helpd, 4 * (size_t)nrep); DA(d.hpart, (size_t)nrep * 4 * h->threads);
       h->grid += d.nhelp;
@@ -2514,7 +2547,7 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   if (!h->have_state || !h->have_labels) return fail(NM_ESTATE, "nm_run_cycle: state and labels must be uploaded first");
   CK(cudaSetDevice(h->cfg.device));
   {                                                       // queue reset + cost ranks from the last cycle's clocks and this cycle's move kinds
-    const int do_sort = h->d.nrep > 1 && h->d.nrep <= 4096 && (h->d.nseg > 1 || h->d.nrep > h->nsm || h->d.nhelp > 0);
+    const int do_sort = h->d.nrep > 1 && h->d.nrep <= 4096 && (h->d.nseg > 1 || h->d.nrep > h->nsm);
     k_schedule<<<1, 1024, do_sort ? h->d.nrep * (sizeof(unsigned long long) + sizeof(int)) : 0, h->stream>>>(h->d, (long long)cycle, do_sort);
     h->launches++;
     CK(cudaGetLastError());
