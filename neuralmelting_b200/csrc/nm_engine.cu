@@ -36,9 +36,10 @@ constexpr int RED_DOUBLES = 2 * RED_HALF;
 constexpr int BC_DOUBLES = 32;
 constexpr int SHT_DOUBLES = 84;          // 27 x 3 image shifts (+ padding)
 constexpr int HELP_STRIDE = 16;          // ints per helper record: [0] helper attached, [1] last command issued (-1: the chain is finished),
-                                         // [2] last command completed, [3] flags (1 energy / virial, 2 fused kick, 4 per-pair minimum image),
-                                         // [4] list buffer, [5] claimed by a helper, [6..7] in-cutoff ordered pairs of the helper's rows
-                                         // (force-only commands), [8] the owner's estimate of its remaining clocks / 1024
+                                         // [2] last command completed, [3] flags (1 energy / virial, 2 fused kick, 4 per-pair minimum image,
+                                         // 8 inner list rows, 16 outer list rows), [4] list buffer, [5] claimed by a helper, [6..7] in-cutoff
+                                         // ordered pairs of the helper's rows (force-only commands), [8] the owner's estimate of its remaining
+                                         // clocks / 1024, [9..10] cell grid of an outer build (cells per axis, stencil half width)
 constexpr int NSMALL = 768;              // largest N handled by the all-pairs hit-matrix build (SMALL mode: one atom per thread)
 // SMALL mode resolves periodic images with GHOST atoms: the shared position array is extended by the shifted copies of
 // the atoms within the list radius of a box face (up to 7 per atom), and the list stores the index of the copy to use.
@@ -321,6 +322,40 @@ __device__ __forceinline__ ushort4 pack_code(ushort4 v, int code) {
   return v;
 }
 
+// ---- force helpers (LARGE mode). With fewer configurations than SMs (C3: 128 chains on 148 SMs) the spare CTAs of the
+// grid, and every CTA whose own chain has finished, attach themselves to the running chain with the most work left (the
+// owners publish an estimate after every move) and evaluate the force rows [2 * blockDim, N) of its evaluations while the
+// owner does rows [0, 2 * blockDim): the owner publishes its positions (shared -> global x) and a command (release), the
+// helper gathers them into its own shared memory, walks the same list rows with the same arithmetic, writes f (and the
+// kicked v) of its atoms and its per-thread partial sums, and answers (release). After help_quantum commands the helper
+// detaches (it clears the attached flag BEFORE its last answer, so the owner cannot address it again) and chooses anew:
+// helped chains fall back in the ranking, and all chains finish at about the same time. The owner never waits for a
+// helper that has not announced itself, so no CTA depends on another one being resident. Results do not depend on
+// whether, when or by whom a chain is helped: per-atom forces are independent, and the energy / virial / kinetic sums
+// are formed as (rows below the split) + (rows above it) per thread in either case. The same split serves the list
+// builds of a helped chain: rows [2 * blockDim, N) of the outer search (the helper bins the cells itself: the cell order
+// is sorted, hence identical) and of the inner regeneration are independent per atom.
+__device__ __forceinline__ bool help_request(Ctx& cx, int flags, double dtf, int a = 0, int b = 0) {
+  if (threadIdx.x == 0) cx.ibc[4] = ld_acquire_gpu(cx.help);
+  __syncthreads();
+  if (cx.ibc[4] != 1) return false;
+  store_positions(cx);
+  cx.help_seq++;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cx.help[3] = flags; cx.help[4] = cx.lbuf; cx.help[9] = a; cx.help[10] = b;
+    cx.helpd[0] = cx.L; cx.helpd[1] = dtf;
+    st_release_gpu(cx.help + 1, cx.help_seq);
+  }
+  return true;
+}
+// wait for the helper's answer; the barrier that follows the acquire (and its L1 invalidation) publishes it to the CTA
+__device__ __forceinline__ void help_wait(Ctx& cx) {
+  if (threadIdx.x == 0) while (ld_acquire_gpu(cx.help + 2) != cx.help_seq) __nanosleep(64);
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ list construction helpers
 // Per-atom list rows grouped by periodic image. A pair enters when its float32 distance is below the list radius
 // times (1+margin); the margin covers the float32 rounding of the fractional coordinates (<= 2^-24 each, < 4e-6
@@ -335,7 +370,7 @@ __device__ __forceinline__ int cell_of(const float4 p, int nc) {
   const int a = min(nc - 1, (int)(p.x * nc)), b = min(nc - 1, (int)(p.y * nc)), e = min(nc - 1, (int)(p.z * nc));
   return (a * nc + b) * nc + e;
 }
-__device__ int outer_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
+__device__ int outer_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw, int i0, int i1) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double invL = 1.0 / cx.L;
   const bool grouped = !cx.mic;
@@ -344,7 +379,7 @@ __device__ int outer_rows(const Dev& d, Ctx& cx, float rl2f, int nc, int sw) {
   const unsigned cur_s = (unsigned)__cvta_generic_to_shared(cx.gcur + tid), gstep = 2u * (unsigned)nthr;
   uint16_t* ol16 = reinterpret_cast<uint16_t*>(cx.olist);
   int over = 0;
-  for (int i = tid; i < N; i += nthr) {
+  for (int i = i0 + tid; i < i1; i += nthr) {
     const float4 pi = cx.sf[i];
     uint32_t* trow = cx.ltmp + i;                          // scratch entry t of atom i: trow[t * Npad] (coalesced over atoms)
 #pragma unroll
@@ -675,6 +710,46 @@ __device__ void build_small(const Dev& d, Ctx& cx) {
   update_thr(d, cx);
 }
 
+// atoms binned into nc^3 cells (counting sort in shared memory; ascending ids inside a cell, so the order -- and with it
+// the order of every list row -- does not depend on which thread got there first)
+__device__ void bin_cells(Ctx& cx, int nc) {
+  const int N = cx.N, tid = threadIdx.x, nthr = blockDim.x, ncell = nc * nc * nc;
+  for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += nthr) {
+    atomicAdd(&cx.cell_cnt[cell_of(cx.sf[i], nc)], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int per = (ncell + 31) / 32, base = tid * per;
+    int s = 0;
+    for (int q = 0; q < per; q++) if (base + q < ncell) s += cx.cell_cnt[base + q];
+    int incl = s;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
+    int run = incl - s;
+    for (int q = 0; q < per; q++) if (base + q < ncell) { cx.cell_start[base + q] = run; run += cx.cell_cnt[base + q]; }
+    if (tid == 31) cx.cell_start[ncell] = incl;
+  }
+  __syncthreads();
+  for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += nthr) {
+    const int c = cell_of(cx.sf[i], nc);
+    int p = atomicAdd(&cx.cell_cnt[c], 1);
+    cx.cell_atoms[cx.cell_start[c] + p] = (uint16_t)i;
+  }
+  __syncthreads();
+  for (int c = tid; c < ncell; c += nthr) {          // ascending ids inside each cell -> deterministic list order
+    const int s = cx.cell_start[c], e = cx.cell_start[c + 1];
+    for (int p = s + 1; p < e; p++) {
+      uint16_t key = cx.cell_atoms[p]; int q = p - 1;
+      while (q >= s && cx.cell_atoms[q] > key) { cx.cell_atoms[q + 1] = cx.cell_atoms[q]; q--; }
+      cx.cell_atoms[q + 1] = key;
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ two-level Verlet lists (deterministic)
 // OUTER list (radius rlo = rc + skin + oskin): cell-binned search on the FP32 pipe, rebuilt rarely. Per atom i it
 // holds neighbour quads GROUPED BY PERIODIC IMAGE: every quad carries one image code (kx+1)*9+(ky+1)*3+(kz+1),
@@ -697,44 +772,11 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
   __syncthreads();
   wrap_and_refresh(cx, true);
   __syncthreads();
-  if (nc > 1) {
-    for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
-    __syncthreads();
-    for (int i = tid; i < N; i += nthr) {
-      atomicAdd(&cx.cell_cnt[cell_of(cx.sf[i], nc)], 1);
-    }
-    __syncthreads();
-    if (tid < 32) {
-      const int per = (ncell + 31) / 32, base = tid * per;
-      int s = 0;
-      for (int q = 0; q < per; q++) if (base + q < ncell) s += cx.cell_cnt[base + q];
-      int incl = s;
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
-      int run = incl - s;
-      for (int q = 0; q < per; q++) if (base + q < ncell) { cx.cell_start[base + q] = run; run += cx.cell_cnt[base + q]; }
-      if (tid == 31) cx.cell_start[ncell] = incl;
-    }
-    __syncthreads();
-    for (int c = tid; c < ncell; c += nthr) cx.cell_cnt[c] = 0;
-    __syncthreads();
-    for (int i = tid; i < N; i += nthr) {
-      const int c = cell_of(cx.sf[i], nc);
-      int p = atomicAdd(&cx.cell_cnt[c], 1);
-      cx.cell_atoms[cx.cell_start[c] + p] = (uint16_t)i;
-    }
-    __syncthreads();
-    for (int c = tid; c < ncell; c += nthr) {          // ascending ids inside each cell -> deterministic list order
-      const int s = cx.cell_start[c], e = cx.cell_start[c + 1];
-      for (int p = s + 1; p < e; p++) {
-        uint16_t key = cx.cell_atoms[p]; int q = p - 1;
-        while (q >= s && cx.cell_atoms[q] > key) { cx.cell_atoms[q + 1] = cx.cell_atoms[q]; q--; }
-        cx.cell_atoms[q + 1] = key;
-      }
-    }
-    __syncthreads();
-  }
+  const bool assisted = cx.help && help_request(cx, 16 | (cx.mic ? 4 : 0), 0.0, nc, sw);      // a helper searches the rows above 2 * blockDim
+  if (nc > 1) bin_cells(cx, nc);
   const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
-  const int over = outer_rows(d, cx, rl2f, nc, sw);
+  int over = outer_rows(d, cx, rl2f, nc, sw, 0, assisted ? 2 * nthr : N);
+  if (assisted) { help_wait(cx); over |= cx.helpd[3] > 0.0; }
   if (__syncthreads_or(over)) cx.status |= ST_NEIGH;
   cx.L0o = L;
   update_thr(d, cx);
@@ -749,15 +791,14 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
 // into a 128-bit shift register (predicated, no branch per candidate); once per outer quad the four oldest entries
 // are emitted as one 8-byte quad. Entries are stored XOR N so that the zero bits of a partial quad read as the dummy.
 template <bool MIC>
-__device__ void build_inner_t(const Dev& d, Ctx& cx) {
+__device__ void inner_rows(const Dev& d, Ctx& cx, int i0, int i1, double& tot, int& over) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
   const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
   const unsigned long long dummy4 = 0x0001000100010001ull * (unsigned long long)N;
   const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf);
   const unsigned rowbytes = (unsigned)Npad * 8u;
-  double tot = 0.0; int over = 0;
-  for (int i = tid; i < N; i += nthr) {
+  for (int i = i0 + tid; i < i1; i += nthr) {
     const float4 pi = cx.sf[i];
     const int nqo = cx.onq[i];
     const char* op = reinterpret_cast<const char*>(cx.olist + i);
@@ -811,11 +852,18 @@ __device__ void build_inner_t(const Dev& d, Ctx& cx) {
     tot += cnt;
     cx.gx0[i] = cx.sp[3 * i] * invL; cx.gx0[Npad + i] = cx.sp[3 * i + 1] * invL; cx.gx0[2 * Npad + i] = cx.sp[3 * i + 2] * invL;
   }
+}
+template <bool MIC>
+__device__ void build_inner_t(const Dev& d, Ctx& cx) {
+  const bool assisted = cx.help && help_request(cx, 8 | (MIC ? 4 : 0), 0.0);      // a helper regenerates the rows above 2 * blockDim
+  double tot = 0.0; int over = 0;
+  inner_rows<MIC>(d, cx, 0, assisted ? 2 * (int)blockDim.x : cx.N, tot, over);
   double r[2] = { tot, (double)over };
   bsum<2>(r, cx);
+  if (assisted) { help_wait(cx); r[0] += cx.helpd[2]; r[1] += cx.helpd[3]; }      // (pair counts: exact in either order)
   cx.list_pairs = 0.5 * r[0];
   if (r[1] > 0.0) cx.status |= ST_NEIGH;
-  cx.L0 = L;
+  cx.L0 = cx.L;
   update_thr(d, cx);
 }
 __device__ void build_inner(const Dev& d, Ctx& cx) {
@@ -1016,38 +1064,6 @@ __device__ __forceinline__ void force_rows(const Dev& d, Ctx& cx, double dtf, in
       if (EW) ke += vx * vx + vy * vy + vz * vz;
     }
   }
-}
-
-// ---- force helpers (LARGE mode). With fewer configurations than SMs (C3: 128 chains on 148 SMs) the spare CTAs of the
-// grid, and every CTA whose own chain has finished, attach themselves to the running chain with the most work left (the
-// owners publish an estimate after every move) and evaluate the force rows [2 * blockDim, N) of its evaluations while the
-// owner does rows [0, 2 * blockDim): the owner publishes its positions (shared -> global x) and a command (release), the
-// helper gathers them into its own shared memory, walks the same list rows with the same arithmetic, writes f (and the
-// kicked v) of its atoms and its per-thread partial sums, and answers (release). After help_quantum commands the helper
-// detaches (it clears the attached flag BEFORE its last answer, so the owner cannot address it again) and chooses anew:
-// helped chains fall back in the ranking, and all chains finish at about the same time. The owner never waits for a
-// helper that has not announced itself, so no CTA depends on another one being resident. Results do not depend on
-// whether, when or by whom a chain is helped: per-atom forces are independent, and the energy / virial / kinetic sums
-// are formed as (rows below the split) + (rows above it) per thread in either case.
-__device__ __forceinline__ bool help_request(Ctx& cx, int flags, double dtf) {
-  if (threadIdx.x == 0) cx.ibc[4] = ld_acquire_gpu(cx.help);
-  __syncthreads();
-  if (cx.ibc[4] != 1) return false;
-  store_positions(cx);
-  cx.help_seq++;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    cx.help[3] = flags; cx.help[4] = cx.lbuf;
-    cx.helpd[0] = cx.L; cx.helpd[1] = dtf;
-    st_release_gpu(cx.help + 1, cx.help_seq);
-  }
-  return true;
-}
-// wait for the helper's answer; the barrier that follows the acquire (and its L1 invalidation) publishes it to the CTA
-__device__ __forceinline__ void help_wait(Ctx& cx) {
-  if (threadIdx.x == 0) while (ld_acquire_gpu(cx.help + 2) != cx.help_seq) __nanosleep(64);
-  __syncthreads();
 }
 
 // EW: also energy / virial / pair count (block-reduced into out[0..2]); KICK: fused second velocity-Verlet
@@ -1857,6 +1873,23 @@ __device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
     if (tid == 0) cx.s_pairs[0] = 0ull;
     __syncthreads();
     double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
+    if (flags & 24) {                                    // list build: the rows above the split of the outer search / the inner regeneration
+      wrap_and_refresh(cx, false);                       // float32 fractional copies (the owner has wrapped the atoms already)
+      __syncthreads();
+      double r[2] = { 0.0, 0.0 };
+      if (flags & 16) {
+        const int nc = hs[9], sw = hs[10];
+        const double rlo = d.rc + d.skin + d.oskin, invL = 1.0 / cx.L;
+        if (nc > 1) bin_cells(cx, nc);
+        r[1] = (double)outer_rows(d, cx, (float)(rlo * rlo * invL * invL * (1.0 + 2e-5)), nc, sw, Ns, N);
+      } else {
+        int over = 0;
+        if (cx.mic) inner_rows<true>(d, cx, Ns, N, r[0], over); else inner_rows<false>(d, cx, Ns, N, r[0], over);
+        r[1] = (double)over;
+      }
+      bsum<2>(r, cx);
+      if (tid == 0) { d.helpd[4 * (size_t)c + 2] = r[0]; d.helpd[4 * (size_t)c + 3] = r[1]; }
+    } else
     switch (flags & 7) {
       case 1: force_rows<true, false, 0, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
       case 2: force_rows<false, true, 0, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
@@ -1866,7 +1899,8 @@ __device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
       case 7: force_rows<true, true, 1, true>(d, cx, dtf, Ns, N, e, vir, ke, np); break;
       default: break;
     }
-    if (flags & 1) { hp[tid] = e; hp[NTHR + tid] = vir; hp[2 * NTHR + tid] = (double)np; hp[3 * NTHR + tid] = ke; }
+    if (flags & 24) { }
+    else if (flags & 1) { hp[tid] = e; hp[NTHR + tid] = vir; hp[2 * NTHR + tid] = (double)np; hp[3 * NTHR + tid] = ke; }
     else {
       np = __reduce_add_sync(0xffffffffu, np);
       if ((tid & 31) == 0) atomicAdd(cx.s_pairs, (unsigned long long)np);
@@ -1875,7 +1909,7 @@ __device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-      if (!(flags & 1)) *reinterpret_cast<unsigned long long*>(hs + 6) = cx.s_pairs[0];
+      if (!(flags & 25)) *reinterpret_cast<unsigned long long*>(hs + 6) = cx.s_pairs[0];
       if (leave) st_release_gpu(hs, 0);                  // detached before the answer: the owner will not address this CTA again
       st_release_gpu(hs + 2, seq);
       if (leave) st_release_gpu(hs + 5, 0);              // the chain may be claimed again

@@ -206,10 +206,12 @@ def test_cycle_parity_n4000_the_north_star_kernel(nm, orc, bulk, skin_outer):
         assert ct["list_builds"] > ct["outer_builds"] >= 3        # inner regenerations from a surviving outer list
 
 
-def test_force_helpers_change_nothing(nm, orc, monkeypatch):
+@pytest.mark.parametrize("skin_outer", [0.0, 0.25])
+def test_force_helpers_change_nothing(nm, orc, monkeypatch, skin_outer):
     """LARGE mode with spare CTA slots: CTAs without a chain evaluate the upper force rows of a running chain
     (nm_engine.cu, help_request / helper_serve). Thermo, state and counters must be bit-identical to a run without
-    helpers (NM_NO_HELPERS=1), and the helped run must really have shared evaluations."""
+    helpers (NM_NO_HELPERS=1), and the helped run must really have shared evaluations. skin_outer = 0.25 forces outer rebuilds inside
+    the run, so that helped outer searches and inner regenerations are covered as well as helped force rows."""
     n_side, n = 10, 4000
     rho, temps, press = [1.1, 0.95, 0.6], [0.4, 1.2, 2.5], [4, 3, 2]
     x, box = _configs(orc, n_side, rho, [0.05] * 3, seed=11)
@@ -221,7 +223,7 @@ def test_force_helpers_change_nothing(nm, orc, monkeypatch):
             monkeypatch.setenv("NM_NO_HELPERS", "1")
         else:
             monkeypatch.delenv("NM_NO_HELPERS", raising=False)
-        with nm.Engine(natoms=n, n_rep=3, nt=3, mod=10, bulk_move=True, seed=7, ppos=0.2, pvol=0.2) as eng:
+        with nm.Engine(natoms=n, n_rep=3, nt=3, mod=10, bulk_move=True, seed=7, ppos=0.2, pvol=0.2, skin_outer=skin_outer) as eng:
             eng.set_labels(T, P / T, T, T)
             eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(3, 0.004), dv=np.full(3, 0.01), dt=np.full(3, 0.006))
             ths = []
@@ -231,6 +233,8 @@ def test_force_helpers_change_nothing(nm, orc, monkeypatch):
         out.append((np.array(ths), st, ct))
     (th_a, st_a, ct_a), (th_b, st_b, ct_b) = out
     assert ct_a["helped_evals"] > 0 and ct_b["helped_evals"] == 0
+    if skin_outer > 0:
+        assert ct_a["outer_builds"] > 3
     np.testing.assert_array_equal(th_a, th_b)
     for k in ("x", "v", "box", "dx", "dv", "dt"):
         np.testing.assert_array_equal(st_a[k], st_b[k])
