@@ -2446,7 +2446,8 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     // force helpers: LARGE mode with rows above 2 * blockDim, one segment per cycle, spare CTA slots (NM_NO_HELPERS: off;
     // NM_HELPERS=n: at most n). The grid grows by the helpers; all of it fits the device at once.
     d.nhelp = 0;
-    if (!d.small && !d.f32 && h->threads == 1024 && N > 2 * h->threads && d.nseg == 1 && nrep < slots && !getenv("NM_NO_HELPERS")) {
+    // (not for iterative single-atom sweeps or very short cycles: few full evaluations per launch, the hand-shakes would cost more than they save)
+    if (!d.small && !d.f32 && h->threads == 1024 && N > 2 * h->threads && d.nseg == 1 && nrep < slots && d.bulk && d.mod >= 4 && !getenv("NM_NO_HELPERS")) {
       long long nh = slots - nrep;
       if (nh > nrep) nh = nrep;
       if (const char* ev = getenv("NM_HELPERS")) { const long long lim = atoll(ev); if (lim >= 0 && lim < nh) nh = lim; }
