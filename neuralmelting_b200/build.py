@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     units = []
     for src in sources():
         if os.path.basename(src) == "nm_engine.cu":      # NM_TU: one unit per thread count + the host unit, built in parallel
-            units += [(src, ["-DNM_TU=%d" % t], ".tu%d" % t) for t in (512, 1024, 256, 0)]
+            units += [(src, ["-DNM_TU=%d" % t], ".tu%d" % t) for t in (1025, 1024, 512, 256, 0)]     # 1025: the helper-capable 1024-thread cycle kernel
         else:
             units.append((src, [], ""))
     for src, defs, tag in units:

@@ -20,6 +20,18 @@
 #include "nm_b200.h"
 #include "nm_device.cuh"
 
+// Helper-capable variant of the 1024-thread cycle kernel (see help_request). It is compiled as a kernel of its own
+// (translation unit NM_TU=1025, symbol k_cycle_h) so that the plain kernels keep their register allocation: with the
+// helper code inlined into the one k_cycle<1024>, ptxas' allocation of the ordered-commit loop of the iterative sweeps
+// changed and C4 ran 19 % slower. The host launches k_cycle_h only when helpers are enabled (d.nhelp > 0).
+#if defined(NM_TU) && NM_TU == 1025
+#define NM_HELPERS 1
+#define k_cycle k_cycle_h
+#elif defined(NM_TU)
+#define NM_HELPERS 0
+#else
+#define NM_HELPERS 1
+#endif
 #ifndef NM_UNR
 #define NM_UNR 1
 #endif
@@ -170,6 +182,7 @@ __host__ __device__ inline size_t smem_bytes(int Npad, int N, int small, int nth
 }
 
 namespace {   // device functions: internal linkage (this file is compiled as several translation units, see NM_TU)
+constexpr bool kHelpers = NM_HELPERS != 0;
 
 // gpu-scope acquire load / release store (segment hand-over of the persistent kernel, force helpers). ptxas follows every
 // acquire load with CCTL.IVALL: the SM's L1 is dropped, so plain loads issued after a barrier see the other SM's writes.
@@ -772,7 +785,7 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
   __syncthreads();
   wrap_and_refresh(cx, true);
   __syncthreads();
-  const bool assisted = cx.help && help_request(cx, 16 | (cx.mic ? 4 : 0), 0.0, nc, sw);      // a helper searches the rows above 2 * blockDim
+  const bool assisted = kHelpers && cx.help && help_request(cx, 16 | (cx.mic ? 4 : 0), 0.0, nc, sw);      // a helper searches the rows above 2 * blockDim
   if (nc > 1) bin_cells(cx, nc);
   const float rl2f = (float)(rlo * rlo * invL * invL * (1.0 + 2e-5));
   int over = outer_rows(d, cx, rl2f, nc, sw, 0, assisted ? 2 * nthr : N);
@@ -855,7 +868,7 @@ __device__ void inner_rows(const Dev& d, Ctx& cx, int i0, int i1, double& tot, i
 }
 template <bool MIC>
 __device__ void build_inner_t(const Dev& d, Ctx& cx) {
-  const bool assisted = cx.help && help_request(cx, 8 | (MIC ? 4 : 0), 0.0);      // a helper regenerates the rows above 2 * blockDim
+  const bool assisted = kHelpers && cx.help && help_request(cx, 8 | (MIC ? 4 : 0), 0.0);      // a helper regenerates the rows above 2 * blockDim
   double tot = 0.0; int over = 0;
   inner_rows<MIC>(d, cx, 0, assisted ? 2 * (int)blockDim.x : cx.N, tot, over);
   double r[2] = { tot, (double)over };
@@ -1080,7 +1093,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
   if (S32 && IMG != 2) {
     // rows above the split are summed separately (see the helper note above); the split depends on N alone
     const int Ns = (!d.small && N > 2 * (int)blockDim.x) ? 2 * (int)blockDim.x : N;
-    if (Ns < N && cx.help) assisted = help_request(cx, (EW ? 1 : 0) | (KICK ? 2 : 0) | (IMG == 1 ? 4 : 0), dtf);
+    if (kHelpers && Ns < N && cx.help) assisted = help_request(cx, (EW ? 1 : 0) | (KICK ? 2 : 0) | (IMG == 1 ? 4 : 0), dtf);
     const int nparts = (Ns < N && !assisted) ? 2 : 1;
 #pragma unroll 1
     for (int part = 0; part < nparts; part++) {
@@ -1088,7 +1101,7 @@ __device__ void eval_forces_t(const Dev& d, Ctx& cx, double dtf, double (&out)[4
       force_rows<EW, KICK, IMG, S32>(d, cx, dtf, part ? Ns : 0, part ? N : Ns, pe, pv, pk, np);
       if (part == 0) { e = pe; vir = pv; ke = pk; } else { e1 = pe; vir1 = pv; ke1 = pk; }
     }
-    if (assisted) {
+    if (kHelpers && assisted) {
       help_wait(cx);
 #if !defined(NM_DEBUG_CLOCKS) && !defined(NM_DEBUG_SMID)     // (the debug builds keep other figures in this column)
       if (threadIdx.x == 0) cx.ct[NM_CT_HELPED_EVALS]++;
@@ -1842,7 +1855,7 @@ k_eval(Dev d, double* pe_out, double* w_out, double* f_out_aos, long long* npair
 // A CTA without a chain of its own serves configuration c (which it has claimed) for up to help_quantum commands or
 // until that chain is finished (see the note at help_request).
 template <int NTHR>
-__device__ void helper_serve(const Dev& d, unsigned char* smem, int c) {
+__device__ __noinline__ void helper_serve(const Dev& d, unsigned char* smem, int c) {      // (out of line: the owner's code keeps its registers)
   Ctx cx; ctx_init(d, cx, c, smem);
   int* hs = d.help + (size_t)HELP_STRIDE * c;
   const double* hd = d.helpd + 4 * (size_t)c;
@@ -1962,7 +1975,7 @@ k_cycle(Dev d, long long cycle) {
     const int ticket = s_ticket;
     if (ticket >= ntickets) {
       // no chain left: help the running chain with the most work left (claims are exclusive), until every chain is finished
-      if constexpr (NTHR == 1024) for (; d.nhelp > 0;) {
+      if constexpr (kHelpers && NTHR == 1024) for (; d.nhelp > 0;) {
         __syncthreads();
         if (threadIdx.x == 0) {
           int c = -1;
@@ -1991,7 +2004,7 @@ k_cycle(Dev d, long long cycle) {
       __syncthreads();
     }
     Ctx cx; ctx_init(d, cx, c, smem);
-    if (NTHR == 1024 && d.nhelp > 0) { cx.help = d.help + (size_t)HELP_STRIDE * c; cx.helpd = d.helpd + 4 * (size_t)c; cx.hpart = d.hpart + (size_t)c * 4 * NTHR; }
+    if (kHelpers && NTHR == 1024 && d.nhelp > 0) { cx.help = d.help + (size_t)HELP_STRIDE * c; cx.helpd = d.helpd + 4 * (size_t)c; cx.hpart = d.hpart + (size_t)c * 4 * NTHR; }
     const int slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
     const long long t_seg0 = clock64();
     const double et = d.label[4 * slot], pf = d.label[4 * slot + 1], t_vel = d.label[4 * slot + 3];
@@ -2017,7 +2030,7 @@ k_cycle(Dev d, long long cycle) {
       if (threadIdx.x == 0) {
         const long long t_now = clock64();
         cx.ct[NM_CT_SWEEPS]++; kclk[kind] += (unsigned long long)(t_now - t_mv0); kcnt[kind]++;
-        if (cx.help) {                                   // remaining clocks at the pace so far (helpers rank the chains by it)
+        if (kHelpers && cx.help) {                       // remaining clocks at the pace so far (helpers rank the chains by it)
           const long long rem = (t_now - t_seg0) / (mv - mv0 + 1) * (mv1 - mv - 1);
           *reinterpret_cast<volatile int*>(cx.help + 8) = (int)min(rem >> 10, 0x7fffffffll);
         }
@@ -2078,7 +2091,7 @@ k_cycle(Dev d, long long cycle) {
     __syncthreads();                                    // ... for every thread of the CTA, before thread 0 publishes the segment
     if (threadIdx.x == 0) {
       st_release_gpu(&d.sched[1 + c], seg + 1);
-      if (cx.help) { st_release_gpu(cx.help + 1, -1); atomicAdd(d.sched + 3 + d.nrep + SMID_MAX, 1); }   // dismiss the helper; one chain fewer to help
+      if (kHelpers && cx.help) { st_release_gpu(cx.help + 1, -1); atomicAdd(d.sched + 3 + d.nrep + SMID_MAX, 1); }   // dismiss the helper; one chain fewer to help
     }
   }
 }
@@ -2122,6 +2135,12 @@ k_velinit(Dev d, long long tag) {
   void launch_velinit_##T(const Dev& d, long long tag, size_t sm, cudaStream_t st);                                  \
   void launch_eval_##T(const Dev& d, double* pe, double* w, double* f, long long* np_, size_t sm, cudaStream_t st);
 NM_LAUNCHER_DECLS(256) NM_LAUNCHER_DECLS(512) NM_LAUNCHER_DECLS(1024)
+cudaError_t set_smem_1024h(size_t sm);
+void launch_cycle_1024h(const Dev& d, long long cycle, int grid, size_t sm, cudaStream_t st);
+#if !defined(NM_TU) || NM_TU == 1025      // the helper-capable cycle kernel (k_cycle_h; the one k_cycle<1024> in a single-unit build)
+cudaError_t set_smem_1024h(size_t sm) { return cudaFuncSetAttribute(k_cycle<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); }
+void launch_cycle_1024h(const Dev& d, long long cycle, int grid, size_t sm, cudaStream_t st) { k_cycle<1024><<<grid, 1024, sm, st>>>(d, cycle); }
+#endif
 #if !defined(NM_TU) || NM_TU == 256
 NM_LAUNCHERS(256)
 #endif
@@ -2422,6 +2441,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   cudaError_t e = cudaSuccess;
   const int sm = (int)h->smem;
   e = h->threads == 256 ? set_smem_256(h->smem) : (h->threads == 512 ? set_smem_512(h->smem) : set_smem_1024(h->smem));
+  if (e == cudaSuccess && h->threads == 1024) e = set_smem_1024h(h->smem);
   if (e != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "cudaFuncSetAttribute(smem=%zu): %s", h->smem, cudaGetErrorString(e)); }
   {
     // persistent cycle kernel: every CTA of the grid must be resident (a CTA may wait for a segment held by another one)
@@ -2589,6 +2609,7 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   }
   if (h->threads == 256) launch_cycle_256(h->d, (long long)cycle, h->grid, h->smem, h->stream);
   else if (h->threads == 512) launch_cycle_512(h->d, (long long)cycle, h->grid, h->smem, h->stream);
+  else if (h->d.nhelp > 0) launch_cycle_1024h(h->d, (long long)cycle, h->grid, h->smem, h->stream);
   else launch_cycle_1024(h->d, (long long)cycle, h->grid, h->smem, h->stream);
   h->launches++;
   CK(cudaGetLastError());

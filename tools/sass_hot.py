@@ -2,7 +2,7 @@
 import re, subprocess, sys
 from collections import Counter
 nthr = sys.argv[1] if len(sys.argv) > 1 else "512"
-out = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2nm7k_cycleILi%sEEEvNS_3DevEx" % nthr, "neuralmelting_b200/libnm_b200.so"], capture_output=True, text=True).stdout
+out = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2nm7k_cycleILi%sEEEvNS_3DevEx" % nthr, sys.argv[2] if len(sys.argv) > 2 else "neuralmelting_b200/libnm_b200.so"], capture_output=True, text=True).stdout
 ins = []
 for l in out.splitlines():
     m = re.match(r'\s+/\*([0-9a-f]+)\*/\s+(.*?);', l)
