@@ -16,7 +16,7 @@ _STAMP = os.path.join(_HERE, ".libnm_b200.stamp")
 EXTRA = os.environ.get("NM_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-diag-suppress=177,550",      # unused helpers / variables of the other translation units
 ]
 
 
