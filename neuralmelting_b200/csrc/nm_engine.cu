@@ -354,7 +354,7 @@ __device__ __forceinline__ bool help_request(Ctx& cx, int flags, double dtf, int
   if (cx.ibc[4] != 1) return false;
   store_positions(cx);
   cx.help_seq++;
-  __threadfence();
+  __threadfence();                                       // (measured: free; the barrier + thread 0's release would do by cumulativity)
   __syncthreads();
   if (threadIdx.x == 0) {
     cx.help[3] = flags; cx.help[4] = cx.lbuf; cx.help[9] = a; cx.help[10] = b;
@@ -1882,7 +1882,19 @@ __device__ __noinline__ void helper_serve(const Dev& d, unsigned char* smem, int
     cx.L = hd[0]; cx.mic = (flags >> 2) & 1;
     const double dtf = hd[1];
     if (tid < 27) { cx.sht[3 * tid] = (tid / 9 - 1) * cx.L; cx.sht[3 * tid + 1] = ((tid / 3) % 3 - 1) * cx.L; cx.sht[3 * tid + 2] = (tid % 3 - 1) * cx.L; }
-    for (int i = tid; i < N; i += NTHR) { cx.sp[3 * i] = __ldcg(cx.gx + i); cx.sp[3 * i + 1] = __ldcg(cx.gx + Npad + i); cx.sp[3 * i + 2] = __ldcg(cx.gx + 2 * Npad + i); }
+    for (int i0 = 0; i0 < N; i0 += 4 * NTHR) {           // positions global (L2) -> shared: twelve loads in flight per thread
+      double px[4], py[4], pz[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * NTHR + tid;
+        if (i < N) { px[u] = __ldcg(cx.gx + i); py[u] = __ldcg(cx.gx + Npad + i); pz[u] = __ldcg(cx.gx + 2 * Npad + i); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * NTHR + tid;
+        if (i < N) { cx.sp[3 * i] = px[u]; cx.sp[3 * i + 1] = py[u]; cx.sp[3 * i + 2] = pz[u]; }
+      }
+    }
     if (tid == 0) cx.s_pairs[0] = 0ull;
     __syncthreads();
     double e = 0.0, vir = 0.0, ke = 0.0; int np = 0;
