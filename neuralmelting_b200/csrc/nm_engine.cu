@@ -101,7 +101,8 @@ struct Dev {
   int* order;                              // [nrep] ticket (within a segment) -> configuration, cheapest first
   int* sched;                              // work queue of the persistent cycle kernel (reset by k_schedule before every launch):
                                            // [0] next ticket, [1 + c] segments of configuration c that are complete,
-                                           // [1 + nrep] CTAs arrived, [2 + nrep] placement invalid, [3 + nrep + smid] CTAs on SM smid
+                                           // [1 + nrep] CTAs arrived, [2 + nrep] placement invalid, [3 + nrep + smid] CTAs on SM smid,
+                                           // [3 + nrep + SMID_MAX] chains finished, [4 + nrep + SMID_MAX] chains started (helpers)
   int nseg, seg_moves;                     // a cycle is cut into nseg segments of seg_moves moves (the unit of scheduling)
   int place;                               // 1: first ticket of every CTA from the SM-aware placement (placement_rank)
   // force helpers (LARGE mode, fewer configurations than CTA slots): CTAs without a chain of their own evaluate the
@@ -1992,6 +1993,11 @@ k_cycle(Dev d, long long cycle) {
         if (threadIdx.x == 0) {
           int c = -1;
           const int* finished = d.sched + 3 + d.nrep + SMID_MAX;
+          // only a chain that is RUNNING may be waited for: if some chains have not started within ~100 us, the grid is not
+          // fully resident (the device is shared) and this CTA makes room instead of holding an SM
+          const int* started = finished + 1;
+          for (int tries = 0; ld_acquire_gpu(started) < d.nrep && tries < 400; tries++) __nanosleep(250);
+          if (ld_acquire_gpu(started) >= d.nrep)
           while (ld_acquire_gpu(finished) < d.nrep) {
             int best = -1, bestrem = 0;
             for (int o = 0; o < d.nrep; o++) {
@@ -2016,6 +2022,7 @@ k_cycle(Dev d, long long cycle) {
       __syncthreads();
     }
     Ctx cx; ctx_init(d, cx, c, smem);
+    if (kHelpers && NTHR == 1024 && d.nhelp > 0 && threadIdx.x == 0) atomicAdd(d.sched + 4 + d.nrep + SMID_MAX, 1);   // this chain is running
     if (kHelpers && NTHR == 1024 && d.nhelp > 0) { cx.help = d.help + (size_t)HELP_STRIDE * c; cx.helpd = d.helpd + 4 * (size_t)c; cx.hpart = d.hpart + (size_t)c * 4 * NTHR; }
     const int slot = d.cfg_slot[c], N = cx.N, Npad = cx.Npad;
     const long long t_seg0 = clock64();
@@ -2172,7 +2179,7 @@ NM_LAUNCHERS(1024)
 __global__ void k_schedule(Dev d, long long cycle, int do_sort) {
   extern __shared__ unsigned long long sclk[];
   int* sorted = reinterpret_cast<int*>(sclk + d.nrep);
-  for (int c = threadIdx.x; c < 4 + d.nrep + SMID_MAX; c += blockDim.x) d.sched[c] = (c == 0 && d.place) ? d.nrep : 0;   // placement hands out the first nrep tickets
+  for (int c = threadIdx.x; c < 5 + d.nrep + SMID_MAX; c += blockDim.x) d.sched[c] = (c == 0 && d.place) ? d.nrep : 0;   // placement hands out the first nrep tickets
   if (d.nhelp > 0) for (int c = threadIdx.x; c < HELP_STRIDE * d.nrep; c += blockDim.x)      // helper records; first ranking: last cycle's clocks
     d.help[c] = (c % HELP_STRIDE) == 8 ? (int)min((d.cta_clk[c / HELP_STRIDE] >> 10) + 1ull, 0x7fffffffull) : 0;
   if (!do_sort) { for (int c = threadIdx.x; c < d.nrep; c += blockDim.x) d.order[c] = c; return; }
@@ -2432,7 +2439,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.x0o, per); DA(d.L0o, nrep);
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
-  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.cost, 2 * (size_t)nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep); DA(d.sched, (size_t)nrep + 4 + SMID_MAX);
+  DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.cost, 2 * (size_t)nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep); DA(d.sched, (size_t)nrep + 5 + SMID_MAX);
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
