@@ -32,6 +32,9 @@
 #else
 #define NM_HELPERS 1
 #endif
+#ifndef NM_BUILD_COST
+#define NM_BUILD_COST 0.25      // SMALL-mode list build in units of one listed-pair evaluation, / N^2 (97 k clocks against 1.57 per pair at N = 500)
+#endif
 #ifndef NM_UNR
 #define NM_UNR 1
 #endif
@@ -105,6 +108,7 @@ struct Dev {
                                            // [3 + nrep + SMID_MAX] chains finished, [4 + nrep + SMID_MAX] chains started (helpers)
   int nseg, seg_moves;                     // a cycle is cut into nseg segments of seg_moves moves (the unit of scheduling)
   int place;                               // 1: first ticket of every CTA from the SM-aware placement (placement_rank)
+  double build_cost;                       // SMALL-mode list build in units of one listed-pair evaluation, / N^2 (cost ranks of the placement)
   // force helpers (LARGE mode, fewer configurations than CTA slots): CTAs without a chain of their own evaluate the
   // upper half of the force rows of a running chain (see helper_serve)
   int nhelp;                               // CTAs launched beyond nrep (0: off)
@@ -2094,7 +2098,7 @@ k_cycle(Dev d, long long cycle) {
       // work estimate in units of one listed pair: evaluations + list builds (SMALL: all-pairs tiles + row walk; LARGE, measured
       // at N = 4000: an inner build ~ 75 N, an outer build ~ 650 N pair evaluations)
       d.cost[2 * c] = (seg ? d.cost[2 * c] : 0ull) + cx.ct[NM_CT_LIST_PAIRS] +
-                      (d.small ? cx.ct[NM_CT_LIST_BUILDS] * (unsigned long long)(0.3 * N * N)
+                      (d.small ? cx.ct[NM_CT_LIST_BUILDS] * (unsigned long long)(d.build_cost * N * N)
                                : (cx.ct[NM_CT_LIST_BUILDS] * 75ull + cx.ct[NM_CT_OUTER_BUILDS] * 650ull) * (unsigned long long)N);
       d.cost[2 * c + 1] = (seg ? d.cost[2 * c + 1] : 0ull) + cx.ct[NM_CT_FORCE_EVALS];
       for (int k = 0; k < 3; k++) d.mv_clk[4 * c + k] = (seg ? d.mv_clk[4 * c + k] : 0ull) + kclk[k];
@@ -2481,6 +2485,8 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
     d.list_pf = d.small ? -1 : 0;
     if (const char* ev = getenv("NM_LIST_PF")) d.list_pf = atoi(ev);
     if (d.list_pf > LIST_SPARE_ROWS - 2) d.list_pf = LIST_SPARE_ROWS - 2;      // stays inside the spare rows of the list buffer
+    d.build_cost = NM_BUILD_COST;
+    if (const char* ev = getenv("NM_BUILD_COST")) { const double v = atof(ev); if (v > 0) d.build_cost = v; }
     d.place = occ == 2 && nrep > h->nsm && nrep <= slots && h->nsm <= SMID_MAX && !getenv("NM_NO_PLACEMENT");
     // force helpers: LARGE mode with rows above 2 * blockDim, one segment per cycle, spare CTA slots (NM_NO_HELPERS: off;
     // NM_HELPERS=n: at most n). The grid grows by the helpers; all of it fits the device at once.
