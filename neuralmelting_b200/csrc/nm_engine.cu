@@ -109,6 +109,8 @@ struct Dev {
   int nseg, seg_moves;                     // a cycle is cut into nseg segments of seg_moves moves (the unit of scheduling)
   int place;                               // 1: first ticket of every CTA from the SM-aware placement (placement_rank)
   double build_cost;                       // SMALL-mode list build in units of one listed-pair evaluation, / N^2 (cost ranks of the placement)
+  double* skinc;                           // [nrep] list skin of each configuration (SMALL mode: tuned per configuration by k_adapt; d.skin otherwise)
+  int adapt_skin;                          // 1: k_adapt moves skinc one step of 0.025 per cycle towards the cheaper side (see there)
   // force helpers (LARGE mode, fewer configurations than CTA slots): CTAs without a chain of their own evaluate the
   // upper half of the force rows of a running chain (see helper_serve)
   int nhelp;                               // CTAs launched beyond nrep (0: off)
@@ -164,6 +166,7 @@ struct Ctx {
   size_t list_stride;           // quads per list buffer
   int status;
   int redflip;                  // which half of `red` the next block_sum uses
+  double skin;                  // list skin of this configuration
   int* help;                    // this configuration's helper record (nullptr: no helpers -- every kernel but k_cycle in LARGE mode)
   int help_seq;                 // commands issued to the helper so far in this cycle
   double *helpd, *hpart;
@@ -264,6 +267,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.mic = d.micmode[c];
   cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.list_pairs = d.list_pairs[c];
   cx.status = 0;
+  cx.skin = d.skinc[c];
   cx.help = nullptr; cx.help_seq = 0; cx.helpd = nullptr; cx.hpart = nullptr;
   if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; for (int k = 0; k < NM_COUNTER_WIDTH; k++) cx.ct[k] = 0; }
 }
@@ -271,7 +275,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
 // displacement budgets for box L (s = L/L0): inner list complete while s*(rl - 2u) >= rc; the outer list can
 // regenerate a complete inner list while s*(rlo - 2u) >= rl
 __device__ __forceinline__ void update_thr(const Dev& d, Ctx& cx) {
-  const double rl = d.rc + d.skin, rlo = rl + d.oskin;
+  const double rl = d.rc + cx.skin, rlo = rl + d.oskin;
   if (cx.L0 <= 0.0) cx.thr2 = -1.0;
   else {
     const double s = cx.L / cx.L0, thr = 0.5 * (rl - d.rc / s) * (1.0 - 1e-9);
@@ -587,7 +591,7 @@ __device__ __forceinline__ void walk_hit_row(const Dev& d, Ctx& cx, int i, const
 
 __device__ void build_small(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
+  const double L = cx.L, rl = d.rc + cx.skin, invL = 1.0 / L;
   const int W = (N + 31) / 32;
   __syncthreads();
   wrap_and_refresh(cx, true);
@@ -779,7 +783,7 @@ __device__ void bin_cells(Ctx& cx, int nc) {
 // same lattice vector so that a revert stays consistent with the stored image codes.
 __device__ void build_outer(const Dev& d, Ctx& cx) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
-  const double L = cx.L, rlo = d.rc + d.skin + d.oskin, invL = 1.0 / L;
+  const double L = cx.L, rlo = d.rc + cx.skin + d.oskin, invL = 1.0 / L;
   // cells of side >= rlo/2 searched with a 5^3 stencil when the box allows it (fewer candidates per atom than
   // cells of side >= rlo with a 3^3 stencil); all atoms when the box is below 3 rlo
   int sw = 2, nc = (int)floor(2.0 * L / (rlo * (1.0 + 1e-4)));
@@ -811,7 +815,7 @@ __device__ void build_outer(const Dev& d, Ctx& cx) {
 template <bool MIC>
 __device__ void inner_rows(const Dev& d, Ctx& cx, int i0, int i1, double& tot, int& over) {
   const int N = cx.N, Npad = cx.Npad, tid = threadIdx.x, nthr = blockDim.x;
-  const double L = cx.L, rl = d.rc + d.skin, invL = 1.0 / L;
+  const double L = cx.L, rl = d.rc + cx.skin, invL = 1.0 / L;
   const float rl2f = (float)(rl * rl * invL * invL * (1.0 + 2e-5));
   const unsigned long long dummy4 = 0x0001000100010001ull * (unsigned long long)N;
   const unsigned sf_s = (unsigned)__cvta_generic_to_shared(cx.sf);
@@ -1628,7 +1632,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
   int nw = blockDim.x >> 5;              // window: one trial per warp, as long as the correction table fits its scratch
   while (nw > 1 && nw * (nw + 1) > 2 * Npad) nw--;
   const int CS = nw + 1;                 // row stride of the correction table (odd: conflict-free): c(a, b) at corr[a * CS + b]
-  const double rc = d.rc, rc2 = rc * rc, rl = rc + d.skin, rlo = rl + d.oskin, L = cx.L, hL = 0.5 * L, invL = 1.0 / L;
+  const double rc = d.rc, rc2 = rc * rc, rl = rc + cx.skin, rlo = rl + d.oskin, L = cx.L, hL = 0.5 * L, invL = 1.0 / L;
   const double rcg = rc * (1 + 1e-9);
   const int L_hi = __double2hiint(L), L_lo = __double2loint(L), hL_hi = __double2hiint(hL);
   const bool two_level = !d.small;
@@ -1659,7 +1663,7 @@ __device__ void iter_position_mc(const Dev& d, Ctx& cx, const Rng& r, double et,
   // LARGE mode: start the sweep from a fresh inner list unless the current one is all but fresh. A trial may use its inner
   // column while un + um <= skin; with the budget already half spent by earlier moves most trials of the sweep would fall
   // back to the outer column (three passes of the warp instead of one): a rebuild costs ~20 rounds of a 125-round sweep.
-  if (two_level && um > 0.05 * d.skin) { build_list(d, cx); max_displacements(); }
+  if (two_level && um > 0.05 * cx.skin) { build_list(d, cx); max_displacements(); }
   if (threadIdx.x == 0) { cx.bc[10] = 0.0; cx.bc[11] = 0.0; cx.bc[12] = 0.0; }
   double* win = cx.red;
   double* corr = reinterpret_cast<double*>(cx.sf);
@@ -1909,7 +1913,7 @@ __device__ __noinline__ void helper_serve(const Dev& d, unsigned char* smem, int
       double r[2] = { 0.0, 0.0 };
       if (flags & 16) {
         const int nc = hs[9], sw = hs[10];
-        const double rlo = d.rc + d.skin + d.oskin, invL = 1.0 / cx.L;
+        const double rlo = d.rc + cx.skin + d.oskin, invL = 1.0 / cx.L;
         if (nc > 1) bin_cells(cx, nc);
         r[1] = (double)outer_rows(d, cx, (float)(rlo * rlo * invL * invL * (1.0 + 2e-5)), nc, sw, Ns, N);
       } else {
@@ -2229,6 +2233,26 @@ __global__ void k_adapt(Dev d) {
     d.step[3 * c + a] = s;
   }
   for (int a = 0; a < 6; a++) d.cnt[6 * c + a] = 0.0;
+  // List skin of the configuration (SMALL mode; not part of the reference: listed pairs outside the cutoff contribute
+  // exact zeros and the rows keep their ascending order, so the skin reaches the results only through the moment at which
+  // a rebuild re-wraps an atom that has left the box -- last bits). A cold solid hardly ever rebuilds
+  // and pays for every listed pair, a fluid rebuilds once per move: from the last cycle's exact counters, the cost per
+  // evaluation J(s) = listed pairs x ((rc + s) / (rc + s_now))^3 + build cost x builds x (s_now / s) (rebuild counts were
+  // measured to fall as s^-1.1) is compared one step of 0.025 up and down, and the skin moves there if that saves more
+  // than 1 %. The lists of a configuration whose skin changed are dropped (L0 = -1: rebuilt at its next position check).
+  if (d.adapt_skin) {
+    const unsigned long long* ct = d.rep_ct + (size_t)c * NM_COUNTER_WIDTH;
+    const double pairs = (double)ct[NM_CT_LIST_PAIRS], builds = (double)ct[NM_CT_LIST_BUILDS];
+    if (ct[NM_CT_FORCE_EVALS] > 0 && pairs > 0.0) {
+      const double s0 = d.skinc[c], bc = d.build_cost * (double)d.N * (double)d.N, step = 0.025;
+      auto J = [&](double sn) { const double q = (d.rc + sn) / (d.rc + s0); return pairs * q * q * q + bc * builds * (s0 / sn); };
+      const double j0 = J(s0);
+      double sn = s0;
+      if (s0 + step <= 0.5 + 1e-9 && J(s0 + step) < 0.99 * j0) sn = s0 + step;
+      else if (s0 - step >= 0.25 - 1e-9 && J(s0 - step) < 0.99 * j0) sn = s0 - step;
+      if (sn != s0) { d.skinc[c] = sn; d.L0[c] = -1.0; }
+    }
+  }
 }
 
 // exchange payload: (pe + ke, vol) per local slot, as lammps_remcmc.py:791 reads them from STATE
@@ -2410,13 +2434,15 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   // sweep so far (both up to sqrt(3) dx lat ~ 0.23 at the adapted step size) stay inside the skin of a list built at the
   // start of the sweep, and the inner column (31 quads: one pass of a warp) serves every trial.
   d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : (cfg->bulk_move ? 0.3 : 0.5));
+  // SMALL mode, default skin: tuned per configuration between 0.25 and 0.5 (k_adapt); NM_FIXED_SKIN=1 keeps it fixed
+  d.adapt_skin = cfg->skin <= 0 && N <= NSMALL && cfg->precision != 32 && !getenv("NM_FIXED_SKIN");
   // outer skin (LARGE mode only): stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6
   d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 1.3;
   d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);
   {
     // list capacities: neighbours inside the list radius at the densest state we expect (rho* 1.6) plus slack,
     // plus padding of the image groups (at most 8 per atom when the box is >= 2 rlo) to whole quads
-    const double rl = d.rc + d.skin, rlo = rl + d.oskin;
+    const double rl = d.rc + (d.adapt_skin ? 0.5 : d.skin), rlo = rl + d.oskin;      // capacity for the largest skin in use
     int maxnb = (int)(4.18879 * rl * rl * rl * 1.6) + 16, maxnbo = (int)(4.18879 * rlo * rlo * rlo * 1.6) + 16;
     if (maxnb > N - 1) maxnb = N - 1;
     if (maxnbo > N - 1) maxnbo = N - 1;
@@ -2444,6 +2470,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   DA(d.box, nrep); DA(d.pe, nrep); DA(d.w, nrep); DA(d.ke, nrep); DA(d.L0, nrep); DA(d.list_pairs, nrep);
   DA(d.step, 3 * (size_t)nrep); DA(d.cnt, 6 * (size_t)nrep);
   DA(d.cfg_slot, nrep); DA(d.slot_cfg, nrep); DA(d.status, nrep); DA(d.cta_clk, nrep); DA(d.cost, 2 * (size_t)nrep); DA(d.rep_ct, (size_t)nrep * NM_COUNTER_WIDTH); DA(d.mv_clk, (size_t)nrep * 4); DA(d.order, nrep); DA(d.sched, (size_t)nrep + 5 + SMID_MAX);
+  DA(d.skinc, nrep);
   DA(d.label, 4 * (size_t)nrep); DA(d.thermo, (size_t)nrep * NM_THERMO_WIDTH); DA(d.counters, NM_COUNTER_WIDTH);
   DA(h->stage_a, (size_t)nrep * 3 * N); DA(h->stage_b, (size_t)nrep * 3 * N); DA(h->stage_s, (size_t)nrep * 8);
   const int nsg = cfg->n_rep_global;
@@ -2454,6 +2481,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   {
     std::vector<int> id(nrep); for (int k = 0; k < nrep; k++) id[k] = k;
     std::vector<double> neg(nrep, -1.0);
+    { std::vector<double> sk(nrep, d.skin); if (cudaMemcpy(d.skinc, sk.data(), sizeof(double) * nrep, cudaMemcpyHostToDevice) != cudaSuccess) { nm_destroy(h); return fail(NM_ECUDA, "nm_create: init copy failed"); } }
     cudaError_t e1 = cudaMemcpy(d.cfg_slot, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
     cudaError_t e2 = cudaMemcpy(d.slot_cfg, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);
     if (e2 == cudaSuccess) e2 = cudaMemcpy(d.order, id.data(), sizeof(int) * nrep, cudaMemcpyHostToDevice);

@@ -242,6 +242,43 @@ def test_force_helpers_change_nothing(nm, orc, monkeypatch, skin_outer):
         assert ct_a[k] == ct_b[k], k
 
 
+def test_adaptive_skin_changes_nothing(nm, orc, monkeypatch):
+    """SMALL mode tunes the list skin per configuration between cycles (k_adapt: a cold solid wants few listed pairs, a
+    fluid few rebuilds). The physics must not notice: every accept / reject decision identical to a run with the skin
+    fixed (NM_FIXED_SKIN=1) and thermo records / final state equal to rounding (a rebuild re-wraps the atoms that have
+    left the box, so WHEN lists are rebuilt moves last bits: 3e-15 relative after eight cycles), while the listed-pair
+    counters show that the skins really moved."""
+    n_side, n = 5, 500
+    x, box = _configs(orc, n_side, [1.1, 1.0, 0.85, 0.6], [0.05] * 4, seed=11)
+    box = np.array([orc.round6(b) for b in box])
+    T = np.array([0.4, 0.9, 1.6, 2.5], dtype=np.float32).astype(np.float64); P = np.array([1, 3, 5, 8], dtype=np.float32).astype(np.float64)
+    out = []
+    for fixed in (False, True):
+        if fixed:
+            monkeypatch.setenv("NM_FIXED_SKIN", "1")
+        else:
+            monkeypatch.delenv("NM_FIXED_SKIN", raising=False)
+        with nm.Engine(natoms=n, n_rep=4, nt=4, mod=32, bulk_move=True, seed=3) as eng:
+            eng.set_labels(T, P / T, T, T)
+            eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(4, 0.004), dv=np.full(4, 0.02), dt=np.full(4, 0.004))
+            ths = []
+            for cyc in range(8):
+                eng.run_cycle(cyc); ths.append(eng.get_thermo()); eng.adapt(); eng.exchange(cyc)
+            st = eng.get_state(); ct = eng.counters()
+        out.append((np.array(ths), st, ct))
+    (th_a, st_a, ct_a), (th_b, st_b, ct_b) = out
+    np.testing.assert_array_equal(th_a[..., 9:18], th_b[..., 9:18])          # move counters and acceptance ratios: exact
+    np.testing.assert_allclose(th_a[..., :9], th_b[..., :9], rtol=1e-10, atol=1e-10)
+    for k in ("box", "dx", "dv", "dt"):
+        np.testing.assert_array_equal(st_a[k], st_b[k])
+    d = st_a["x"] - st_b["x"]
+    d -= st_a["box"][:, None] * np.rint(d / st_a["box"][:, None])
+    assert np.abs(d).max() < 1e-9 and np.abs(st_a["v"] - st_b["v"]).max() < 1e-9
+    for k in ("force_evals", "pairs_force", "pairs_full", "hmc_atom_steps", "sweeps"):
+        assert ct_a[k] == ct_b[k], k
+    assert ct_a["list_pairs"] != ct_b["list_pairs"]
+
+
 def test_cycle_hmc_only_matches_oracle(nm, orc):
     """pure HMC (ppos = pvol = 0), no text rounding: every trajectory's accept decision and the final energies
     match the oracle; smaller dt conserves H better (the unshifted cutoff adds +-0.0163 per shell crossing)"""
