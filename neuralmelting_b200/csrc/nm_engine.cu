@@ -111,6 +111,7 @@ struct Dev {
   double build_cost;                       // SMALL-mode list build in units of one listed-pair evaluation, / N^2 (cost ranks of the placement)
   double* skinc;                           // [nrep] list skin of each configuration (SMALL mode: tuned per configuration by k_adapt; d.skin otherwise)
   int adapt_skin;                          // 1: k_adapt moves skinc one step of 0.025 per cycle towards the cheaper side (see there)
+  double skin_lo, skin_hi, skin_pow;       // its range and the exponent of the rebuild-count model
   // force helpers (LARGE mode, fewer configurations than CTA slots): CTAs without a chain of their own evaluate the
   // upper half of the force rows of a running chain (see helper_serve)
   int nhelp;                               // CTAs launched beyond nrep (0: off)
@@ -2245,11 +2246,11 @@ __global__ void k_adapt(Dev d) {
     const double pairs = (double)ct[NM_CT_LIST_PAIRS], builds = (double)ct[NM_CT_LIST_BUILDS];
     if (ct[NM_CT_FORCE_EVALS] > 0 && pairs > 0.0) {
       const double s0 = d.skinc[c], bc = d.build_cost * (double)d.N * (double)d.N, step = 0.025;
-      auto J = [&](double sn) { const double q = (d.rc + sn) / (d.rc + s0); return pairs * q * q * q + bc * builds * (s0 / sn); };
+      auto J = [&](double sn) { const double q = (d.rc + sn) / (d.rc + s0); return pairs * q * q * q + bc * builds * pow(s0 / sn, d.skin_pow); };
       const double j0 = J(s0);
       double sn = s0;
-      if (s0 + step <= 0.5 + 1e-9 && J(s0 + step) < 0.99 * j0) sn = s0 + step;
-      else if (s0 - step >= 0.25 - 1e-9 && J(s0 - step) < 0.99 * j0) sn = s0 - step;
+      if (s0 + step <= d.skin_hi + 1e-9 && J(s0 + step) < 0.99 * j0) sn = s0 + step;
+      else if (s0 - step >= d.skin_lo - 1e-9 && J(s0 - step) < 0.99 * j0) sn = s0 - step;
       if (sn != s0) { d.skinc[c] = sn; d.L0[c] = -1.0; }
     }
   }
@@ -2434,15 +2435,17 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   // sweep so far (both up to sqrt(3) dx lat ~ 0.23 at the adapted step size) stay inside the skin of a list built at the
   // start of the sweep, and the inner column (31 quads: one pass of a warp) serves every trial.
   d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : (cfg->bulk_move ? 0.3 : 0.5));
-  // SMALL mode, default skin: tuned per configuration between 0.25 and 0.5 (k_adapt); NM_FIXED_SKIN=1 keeps it fixed
+  // SMALL mode, default skin: tuned per configuration between 0.2 and 0.5 (k_adapt; NM_SKIN_RANGE=lo,hi[,p] for experiments); NM_FIXED_SKIN=1 keeps it fixed
   d.adapt_skin = cfg->skin <= 0 && N <= NSMALL && cfg->precision != 32 && !getenv("NM_FIXED_SKIN");
+  d.skin_lo = 0.2; d.skin_hi = 0.5; d.skin_pow = 1.0;
+  if (const char* ev = getenv("NM_SKIN_RANGE")) { double a = 0, b = 0, c = 0; const int n = sscanf(ev, "%lf,%lf,%lf", &a, &b, &c); if (n >= 2 && a > 0.05 && b >= a && b <= 0.6) { d.skin_lo = a; d.skin_hi = b; } if (n >= 3 && c > 0) d.skin_pow = c; }
   // outer skin (LARGE mode only): stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6
   d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 1.3;
   d.seed_lo = (uint32_t)cfg->seed; d.seed_hi = (uint32_t)(cfg->seed >> 32);
   {
     // list capacities: neighbours inside the list radius at the densest state we expect (rho* 1.6) plus slack,
     // plus padding of the image groups (at most 8 per atom when the box is >= 2 rlo) to whole quads
-    const double rl = d.rc + (d.adapt_skin ? 0.5 : d.skin), rlo = rl + d.oskin;      // capacity for the largest skin in use
+    const double rl = d.rc + (d.adapt_skin ? d.skin_hi : d.skin), rlo = rl + d.oskin;      // capacity for the largest skin in use
     int maxnb = (int)(4.18879 * rl * rl * rl * 1.6) + 16, maxnbo = (int)(4.18879 * rlo * rlo * rlo * 1.6) + 16;
     if (maxnb > N - 1) maxnb = N - 1;
     if (maxnbo > N - 1) maxnbo = N - 1;
