@@ -112,6 +112,7 @@ struct Dev {
   double* skinc;                           // [nrep] list skin of each configuration (SMALL mode: tuned per configuration by k_adapt; d.skin otherwise)
   int adapt_skin;                          // 1: k_adapt moves skinc one step of 0.025 per cycle towards the cheaper side (see there)
   double skin_lo, skin_hi, skin_pow;       // its range and the exponent of the rebuild-count model
+  double inner_cost;                       // LARGE mode: one inner list build in listed-pair evaluations, / N
   // force helpers (LARGE mode, fewer configurations than CTA slots): CTAs without a chain of their own evaluate the
   // upper half of the force rows of a running chain (see helper_serve)
   int nhelp;                               // CTAs launched beyond nrep (0: off)
@@ -2234,7 +2235,7 @@ __global__ void k_adapt(Dev d) {
     d.step[3 * c + a] = s;
   }
   for (int a = 0; a < 6; a++) d.cnt[6 * c + a] = 0.0;
-  // List skin of the configuration (SMALL mode; not part of the reference: listed pairs outside the cutoff contribute
+  // List skin of the configuration (not part of the reference: listed pairs outside the cutoff contribute
   // exact zeros and the rows keep their ascending order, so the skin reaches the results only through the moment at which
   // a rebuild re-wraps an atom that has left the box -- last bits). A cold solid hardly ever rebuilds
   // and pays for every listed pair, a fluid rebuilds once per move: from the last cycle's exact counters, the cost per
@@ -2245,13 +2246,15 @@ __global__ void k_adapt(Dev d) {
     const unsigned long long* ct = d.rep_ct + (size_t)c * NM_COUNTER_WIDTH;
     const double pairs = (double)ct[NM_CT_LIST_PAIRS], builds = (double)ct[NM_CT_LIST_BUILDS];
     if (ct[NM_CT_FORCE_EVALS] > 0 && pairs > 0.0) {
-      const double s0 = d.skinc[c], bc = d.build_cost * (double)d.N * (double)d.N, step = 0.025;
+      // cost of one (inner) list build in listed-pair evaluations: SMALL N^2 tiles + row walk; LARGE ~ 75 N (measured at N = 4000;
+      // the outer searches depend on the outer skin and on diffusion, hardly on this one)
+      const double s0 = d.skinc[c], bc = d.small ? d.build_cost * (double)d.N * (double)d.N : d.inner_cost * (double)d.N, step = 0.025;
       auto J = [&](double sn) { const double q = (d.rc + sn) / (d.rc + s0); return pairs * q * q * q + bc * builds * pow(s0 / sn, d.skin_pow); };
       const double j0 = J(s0);
       double sn = s0;
       if (s0 + step <= d.skin_hi + 1e-9 && J(s0 + step) < 0.99 * j0) sn = s0 + step;
       else if (s0 - step >= d.skin_lo - 1e-9 && J(s0 - step) < 0.99 * j0) sn = s0 - step;
-      if (sn != s0) { d.skinc[c] = sn; d.L0[c] = -1.0; }
+      if (sn != s0) { d.skinc[c] = sn; d.L0[c] = -1.0; if (!d.small) d.L0o[c] = -1.0; }     // (the outer radius is rc + skin + outer skin)
     }
   }
 }
@@ -2436,8 +2439,13 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   // start of the sweep, and the inner column (31 quads: one pass of a warp) serves every trial.
   d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : (cfg->bulk_move ? 0.3 : 0.5));
   // SMALL mode, default skin: tuned per configuration between 0.2 and 0.5 (k_adapt; NM_SKIN_RANGE=lo,hi[,p] for experiments); NM_FIXED_SKIN=1 keeps it fixed
-  d.adapt_skin = cfg->skin <= 0 && N <= NSMALL && cfg->precision != 32 && !getenv("NM_FIXED_SKIN");
-  d.skin_lo = 0.2; d.skin_hi = 0.5; d.skin_pow = 1.0;
+  // (LARGE mode: measured on the C3 shard with 0.2 .. 0.4 around the default 0.3 and inner-build costs of 75 .. 600 N pair
+  // evaluations: 121.5 .. 125.2 ms against 119.3 ms with the fixed skin -- a skin change also drops the outer list, and the
+  // hot chains that set the kernel time are the ones that keep changing; NM_ADAPT_SKIN_LARGE=1 turns it on for experiments)
+  d.adapt_skin = cfg->skin <= 0 && (N <= NSMALL || (cfg->bulk_move && getenv("NM_ADAPT_SKIN_LARGE"))) && cfg->precision != 32 && !getenv("NM_FIXED_SKIN");
+  d.skin_lo = 0.2; d.skin_hi = N <= NSMALL ? 0.5 : 0.4; d.skin_pow = 1.0;
+  d.inner_cost = 75.0;
+  if (const char* ev = getenv("NM_INNER_COST")) { const double v = atof(ev); if (v > 0) d.inner_cost = v; }
   if (const char* ev = getenv("NM_SKIN_RANGE")) { double a = 0, b = 0, c = 0; const int n = sscanf(ev, "%lf,%lf,%lf", &a, &b, &c); if (n >= 2 && a > 0.05 && b >= a && b <= 0.6) { d.skin_lo = a; d.skin_hi = b; } if (n >= 3 && c > 0) d.skin_pow = c; }
   // outer skin (LARGE mode only): stationary N = 4000 grid: 245 ms per cycle at 1.0, 215 at 1.3, 221 at 1.6
   d.oskin = cfg->skin_outer > 0 ? cfg->skin_outer : 1.3;
