@@ -2438,6 +2438,7 @@ int nm_create(const nm_config* cfg, nm_engine** out) {
   // sweep so far (both up to sqrt(3) dx lat ~ 0.23 at the adapted step size) stay inside the skin of a list built at the
   // start of the sweep, and the inner column (31 quads: one pass of a warp) serves every trial.
   d.skin = cfg->skin > 0 ? cfg->skin : (N <= NSMALL ? 0.4 : (cfg->bulk_move ? 0.3 : 0.5));
+  if (const char* ev = getenv("NM_SKIN")) { const double v = atof(ev); if (cfg->skin <= 0 && v > 0.05 && v < 1.0) d.skin = v; }   // experiments: another default
   // SMALL mode, default skin: tuned per configuration between 0.2 and 0.5 (k_adapt; NM_SKIN_RANGE=lo,hi[,p] for experiments); NM_FIXED_SKIN=1 keeps it fixed
   // (LARGE mode: measured on the C3 shard with 0.2 .. 0.4 around the default 0.3 and inner-build costs of 75 .. 600 N pair
   // evaluations: 121.5 .. 125.2 ms against 119.3 ms with the fixed skin -- a skin change also drops the outer list, and the
