@@ -269,7 +269,7 @@ __device__ __forceinline__ void ctx_init(const Dev& d, Ctx& cx, int c, unsigned 
   cx.mic = d.micmode[c];
   cx.L = d.box[c]; cx.L0 = d.L0[c]; cx.list_pairs = d.list_pairs[c];
   cx.status = 0;
-  cx.skin = d.skinc[c];
+  cx.skin = d.adapt_skin ? d.skinc[c] : d.skin;
   cx.help = nullptr; cx.help_seq = 0; cx.helpd = nullptr; cx.hpart = nullptr;
   if (threadIdx.x == 0) { cx.s_pairs[0] = 0; cx.s_pairs[1] = 0; for (int k = 0; k < NM_COUNTER_WIDTH; k++) cx.ct[k] = 0; }
 }
