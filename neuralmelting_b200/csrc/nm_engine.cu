@@ -1559,18 +1559,22 @@ __device__ __noinline__ void commit_window(const double* win, const double* corr
   const unsigned stop = __ballot_sync(0xffffffffu, flag != 0 || !ok);
   const int tmax = stop ? __ffs(stop) - 1 : 32;          // <= nwin: lanes past the window carry flag 3
   const int need = tmax == 0 && __shfl_sync(0xffffffffu, flag, 0) == 1;
-  // ---- the serial chain
+  // ---- the serial chain. Every lane tests ITS OWN trial against its own thresholds at every turn (only lane t's answer
+  // counts at turn t), so what travels between the lanes is one ballot instead of a broadcast double, and the correction
+  // row of the next turn is loaded while this one is decided: the chain is compare -> vote -> add.
   const double floor_ = -600.0 * et;
+  const double lo = mine ? wl[WS_LO] : 0.0, hi = mine ? wl[WS_HI] : 0.0;
   unsigned accmask = 0u;
+  double c_t = corr[lane];                               // c(0, lane)
   for (int t = 0; t < tmax; t++) {
-    const double* wt = win + WS * t;
-    const double de_t = __shfl_sync(0xffffffffu, de, t);
-    const double lo = wt[WS_LO], hi = wt[WS_HI], c_t = corr[t * CS + lane];
+    const double c_next = corr[(t + 1 < tmax ? t + 1 : t) * CS + lane];
+    const unsigned b_acc = __ballot_sync(0xffffffffu, de > floor_ && de < lo), b_rej = __ballot_sync(0xffffffffu, de > hi);
     bool acc;
-    if (de_t > floor_ && de_t < lo) acc = true;
-    else if (de_t > hi) acc = false;
-    else acc = decide_exact(de_t, et, wt[WS_UACC]);
+    if ((b_acc >> t) & 1u) acc = true;
+    else if ((b_rej >> t) & 1u) acc = false;
+    else acc = decide_exact(__shfl_sync(0xffffffffu, de, t), et, win[WS * t + WS_UACC]);      // inside the band: the exact rule
     if (acc) { accmask |= 1u << t; if (lane > t) de += c_t; }
+    c_t = c_next;
   }
   // ---- after: move the accepted atoms (store_pos on the values passed in), update the maxima and the counters
   const bool moved = (accmask >> lane) & 1u;
