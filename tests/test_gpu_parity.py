@@ -242,6 +242,34 @@ def test_force_helpers_change_nothing(nm, orc, monkeypatch, skin_outer):
         assert ct_a[k] == ct_b[k], k
 
 
+def test_helper_schedules_give_one_result(nm, orc, monkeypatch):
+    """Which helper CTA serves which configuration, and for how long, depends on timing and on NM_HELP_QUANTUM /
+    NM_HELPERS; thermo records and final state must be the same bits under every schedule (a race in the hand-shake
+    would show here), while the number of helped evaluations differs."""
+    n_side, n = 10, 4000
+    x, box = _configs(orc, n_side, [1.0, 0.7], [0.04] * 2, seed=5)
+    box = np.array([orc.round6(b) for b in box])
+    T = np.array([0.5, 2.0]); P = np.array([2.0, 2.0])
+    res = []
+    for env in ({"NM_HELP_QUANTUM": "1", "NM_HELPERS": "1"}, {"NM_HELP_QUANTUM": "2", "NM_HELPERS": "2"}, {}, {"NM_NO_HELPERS": "1"}):
+        for k in ("NM_HELP_QUANTUM", "NM_HELPERS", "NM_NO_HELPERS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with nm.Engine(natoms=n, n_rep=2, nt=2, mod=4, bulk_move=True, seed=5, ppos=0.25, pvol=0.25, skin_outer=0.25) as eng:
+            eng.set_labels(T, P / T, T, T)
+            eng.set_state(x=x, v=np.zeros_like(x), box=box, dx=np.full(2, 0.004), dv=np.full(2, 0.01), dt=np.full(2, 0.005))
+            ths = []
+            for cyc in range(2):
+                eng.run_cycle(cyc); ths.append(eng.get_thermo()); eng.adapt(); eng.exchange(cyc)
+            st = eng.get_state(); ct = eng.counters()
+        res.append((np.array(ths), st, ct["helped_evals"]))
+    for th, st, _ in res[1:]:
+        np.testing.assert_array_equal(th, res[0][0])
+        np.testing.assert_array_equal(st["x"], res[0][1]["x"]); np.testing.assert_array_equal(st["v"], res[0][1]["v"])
+    assert res[3][2] == 0 and min(r[2] for r in res[:3]) > 0
+
+
 def test_adaptive_skin_changes_nothing(nm, orc, monkeypatch):
     """SMALL mode tunes the list skin per configuration between cycles (k_adapt: a cold solid wants few listed pairs, a
     fluid few rebuilds). The physics must not notice: every accept / reject decision identical to a run with the skin
