@@ -2678,7 +2678,8 @@ int nm_run_cycle(nm_engine* h, int64_t cycle) {
   }
   if (h->threads == 256) launch_cycle_256(h->d, (long long)cycle, h->grid, h->smem, h->stream);
   else if (h->threads == 512) launch_cycle_512(h->d, (long long)cycle, h->grid, h->smem, h->stream);
-  else if (h->d.nhelp > 0 || getenv("NM_FORCE_HELPER_KERNEL")) launch_cycle_1024h(      // (experiments: the helper-capable kernel without helpers)h->d, (long long)cycle, h->grid, h->smem, h->stream);
+  else if (h->d.nhelp > 0 || getenv("NM_FORCE_HELPER_KERNEL"))      // (the variable: experiments with the helper-capable kernel alone)
+    launch_cycle_1024h(h->d, (long long)cycle, h->grid, h->smem, h->stream);
   else launch_cycle_1024(h->d, (long long)cycle, h->grid, h->smem, h->stream);
   h->launches++;
   CK(cudaGetLastError());
