@@ -128,6 +128,13 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def mc_config(desc, natoms, nloc, npn, nt, mod, world, rows):
+    """the `config` object of an MC workload line: the same for the b200 arm and the reference arm (the driver compares them)"""
+    return {"workload": desc, "natoms": natoms, "replicas_per_gpu": nloc, "grid": [npn, nt], "moves_per_cycle": mod, "hmc_steps": 8,
+            "l2": "inputs larger than L2 (per-GPU state + neighbour lists of %d replicas > 126 MB)" % nloc if nloc * natoms > 60000 else "working set fits L2; no flush (compute-bound on-chip kernel)",
+            "parallelism": "replica grid sharded by pressure row, row u on rank u mod %d (%d row(s)/GPU); swaps decided rank-locally, (pe+ke, vol) all-gathered asynchronously" % (world, rows)}
+
+
 def flops_from(ct):
     """algorithmic FLOPs: 24 per in-cutoff pair (force-only), 30 (force+energy+virial), 2x13 per single-atom
     dE neighbour, 18 per atom-step of the integrator"""
@@ -284,9 +291,7 @@ def measure_mc(args, comm, torch, workload, steps, warmup, equil, with_e2e=True,
             "n_gpus": comm.world, "steps": steps, "warmup": max(3, warmup), "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f32",
             "data": "synthetic: pressure-relaxed fcc + random displacement (the reference's init_sample), %d equilibration cycles, counter-based RNG seed 256" % equil,
-            "config": {"workload": desc, "natoms": natoms, "replicas_per_gpu": nloc, "grid": [npn, nt], "moves_per_cycle": mod,
-                       "hmc_steps": 8, "l2": "inputs larger than L2 (per-GPU state + neighbour lists of %d replicas > 126 MB)" % nloc if nloc * natoms > 60000 else "working set fits L2; no flush (compute-bound on-chip kernel)",
-                       "parallelism": "replica grid sharded by pressure row, row u on rank u mod %d (%d row(s)/GPU); swaps decided rank-locally, (pe+ke, vol) all-gathered asynchronously" % (comm.world, rows)},
+            "config": mc_config(desc, natoms, nloc, npn, nt, mod, comm.world, rows),
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "fp64_fma" if args.precision == 64 else "fp32_fma", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_unit": "bytes/launch (ncu --set full, profiles/%s)" % capture if capture else None,
@@ -445,7 +450,7 @@ def run_reference(args):
             "mc_sweeps_per_sec": tot[orc.CT_SWEEPS] / t, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic: relaxed fcc + random displacement, counter-based RNG seed 256",
-            "config": {"workload": desc, "natoms": natoms, "grid": [npn, nt], "moves_per_cycle": mod},
+            "config": mc_config(desc, natoms, rows * nt, npn, nt, mod, world, rows),      # the b200 arm's config, key for key
             "cpu_baseline": {"value": val, "unit": "atom-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of lammps_remcmc.py's per-replica path (LAMMPS + Dask are not installable here); one replica per task over all host threads"}
